@@ -1,0 +1,81 @@
+"""ctypes binding of libflute_b200.so -- the only way Python reaches the kernels.
+
+There is NO fallback: if the library is missing the import fails loudly, and every entry
+point raises RuntimeError on a non-zero return code (the reference raises through
+AT_ERROR / C10_CUDA_KERNEL_LAUNCH_CHECK, flute/csrc/qgemm.cpp:82,153,171).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflute_b200.so")
+
+# every symbol include/flute_b200.h declares
+EXPORTS = (
+    "flute_b200_qgemm",
+    "flute_b200_qgemm_host",
+    "flute_b200_hadamard",
+    "flute_b200_dequantize",
+    "flute_b200_workspace_bytes",
+    "flute_b200_num_sms",
+    "flute_b200_max_batch_tile",
+    "flute_b200_last_error",
+    "flute_b200_error_string",
+    "flute_b200_version",
+    "flute_b200_set_timeout_ms",
+    "flute_b200_check",
+    "flute_b200_qgemm_debug",
+)
+
+F16, BF16 = 0, 1
+FLAG_PDL = 1
+
+_vp, _i, _sz, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_long
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m flute_b200.build` "
+            "(or __graft_entry__.build()). flute_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.flute_b200_qgemm.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+    lib.flute_b200_qgemm.restype = _i
+    lib.flute_b200_qgemm_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                          _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+    lib.flute_b200_qgemm_host.restype = _i
+    lib.flute_b200_qgemm_debug.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
+                                           _i, _i, _i, _i, _vp]
+    lib.flute_b200_qgemm_debug.restype = _i
+    lib.flute_b200_hadamard.argtypes = [_vp, _vp, _l, _i, _i, _i, _vp]
+    lib.flute_b200_hadamard.restype = _i
+    lib.flute_b200_dequantize.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]
+    lib.flute_b200_dequantize.restype = _i
+    lib.flute_b200_workspace_bytes.argtypes = [_i]
+    lib.flute_b200_workspace_bytes.restype = _sz
+    lib.flute_b200_num_sms.argtypes = [_i]
+    lib.flute_b200_num_sms.restype = _i
+    lib.flute_b200_max_batch_tile.argtypes = [_i]
+    lib.flute_b200_max_batch_tile.restype = _i
+    lib.flute_b200_last_error.argtypes = []
+    lib.flute_b200_last_error.restype = ctypes.c_char_p
+    lib.flute_b200_error_string.argtypes = [_i]
+    lib.flute_b200_error_string.restype = ctypes.c_char_p
+    lib.flute_b200_version.argtypes = []
+    lib.flute_b200_version.restype = _i
+    lib.flute_b200_set_timeout_ms.argtypes = [_l]
+    lib.flute_b200_set_timeout_ms.restype = None
+    lib.flute_b200_check.argtypes = [_i]
+    lib.flute_b200_check.restype = _i
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib.flute_b200_last_error().decode() or lib.flute_b200_error_string(rc).decode()
+        raise RuntimeError(f"flute_b200: {msg} (code {rc})")

@@ -1,0 +1,279 @@
+// Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05
+// (TMEM alloc / st / ld / mma / commit / fences) and programmatic dependent launch.
+// Hand-written for this engine; no CUTLASS/CuTe types are used anywhere in the build.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fb {
+
+// ------------------------------------------------------------------------------------
+// Diagnostics block (pinned, mapped host memory).  A role that times out on a barrier
+// writes what it was waiting for here and traps, so a deadlock becomes a loud launch
+// failure with a readable reason instead of a hung GPU.
+// ------------------------------------------------------------------------------------
+struct Diag {
+    volatile int code;      // 0 = clean
+    volatile int block;
+    volatile int warp;
+    volatile int site;      // which wait
+    volatile int index;     // stage / slot index
+    volatile int parity;
+    volatile int iter;
+    volatile int pad;
+};
+
+enum DiagSite : int {
+    SITE_PROD_EMPTY = 1,
+    SITE_DQ_FULL = 2,
+    SITE_DQ_AEMPTY = 3,
+    SITE_DQ_SCALE = 4,
+    SITE_DQ_ACCFULL = 5,
+    SITE_MMA_FULL = 6,
+    SITE_MMA_AFULL = 7,
+    SITE_MMA_ACCEMPTY = 8,
+    SITE_SC_EMPTY = 9,
+    SITE_FINAL = 10,
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ------------------------------------------------------------------------------------
+// mbarrier
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Bounded wait.  `timeout_ns == 0` disables the bound.
+static __device__ __noinline__ void mbar_timeout(Diag* diag, int site, int index, uint32_t parity, int iter) {
+    if (diag != nullptr) {
+        diag->block = blockIdx.x;
+        diag->warp = threadIdx.x >> 5;
+        diag->site = site;
+        diag->index = index;
+        diag->parity = static_cast<int>(parity);
+        diag->iter = iter;
+        diag->code = 1;
+        __threadfence_system();
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, Diag* diag, uint64_t timeout_ns, int site,
+                                          int index, int iter) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (timeout_ns != 0 && (++spins & 0xfff) == 0) {
+            uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) mbar_timeout(diag, site, index, parity, iter);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// TMA
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// Programmatic dependent launch
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc];  kind::f16 (fp16 or bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// 32 lanes x 32 bit, 32 consecutive columns: thread t <-> TMEM lane (quarter base + t),
+// register i <-> column (base + i).
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+        "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+        "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// Descriptors
+// ------------------------------------------------------------------------------------
+// Instruction descriptor for tcgen05.mma kind::f16: fp32 accumulate, A and B both K-major.
+//   [4,6) D format (1 = f32)  [7,10) A format (0 = f16, 1 = bf16)  [10,13) B format
+//   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3  [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_f16(bool bf16, int mma_m, int mma_n) {
+    return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) |
+           (static_cast<uint32_t>(mma_n >> 3) << 17) | (static_cast<uint32_t>(mma_m >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor, K-major operand in the 128-byte-swizzled canonical
+// layout (rows of 128 B, 8-row groups of 1024 B):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1)
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups)   [46,48) version = 1
+//   [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------
+// T arithmetic on packed pairs (bit patterns in uint32)
+// ------------------------------------------------------------------------------------
+template <bool BF16>
+__device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    if constexpr (BF16) {
+        asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    } else {
+        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    }
+    return r;
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint16_t f32_to_t(float v) {
+    if constexpr (BF16) {
+        return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    } else {
+        return __half_as_ushort(__float2half_rn(v));
+    }
+}
+
+template <bool BF16>
+__device__ __forceinline__ float t_to_f32(uint16_t v) {
+    if constexpr (BF16) {
+        return __bfloat162float(__ushort_as_bfloat16(v));
+    } else {
+        return __half2float(__ushort_as_half(v));
+    }
+}
+
+}  // namespace fb

@@ -1,0 +1,793 @@
+// LUT-quantized GEMM for sm_100a:  D[M,N] = A[M,K] . W_hat[K,N],
+//   W_hat[k,n] = round_T(table2[code(k/2,n)].{lo,hi} * S[n, k/group]).
+//
+// Replaces the reference's qgemm_device / qgemm_host (flute/csrc/qgemm_kernel.hpp:24-939),
+// its register dequantiser (flute/csrc/packbits_utils.hpp:24-427), its Stream-K scheduler
+// and fix-up (flute/csrc/tile_scheduler_utils.hpp:58-1058) with one warp-specialised
+// kernel, runtime-parameterised instead of template-enumerated.  Consumes the reference's
+// packed-weight wire format unchanged (flute/utils.py:59-253).
+//
+// Mapping ("swap-AB"): the WEIGHTS are the tcgen05 "A" operand and live in TENSOR MEMORY;
+// the activations are the "B" operand in shared memory.  One CTA tile is 128 packed rows
+// (TMEM lanes) x one 64-wide K stage.  A packed 32-bit word holds NJ pair-codes that belong to
+// NJ different output columns (NJ = 4 / 8 / 16 for 4 / 2 / 3 bits), so the tile owns NJ
+// accumulators D_j[128 lanes x Mb] and the thread on lane L uses every field of every word
+// it loads: field j of word (L, k2) is dequantised into column k2 of "A_j".  The N
+// permutation the wire format bakes in is undone for free in the epilogue's store address.
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over a contiguous Stream-K range):
+//   warps 0-7   dequantisers (two groups of four; warp%4 = TMEM lane quarter) + epilogue
+//   warp  8     TMA producer (packed-weight tiles + activation tiles, mbarrier ring)
+//   warp  9     tcgen05.mma issuer, TMEM allocator
+//   warps 10-11 scale loaders (global -> smem, group-major so reads are conflict-free)
+#include "ptx.cuh"
+#include "qgemm_sm100.h"
+
+#include <cuda.h>
+#include <stdio.h>
+
+namespace fb {
+
+// ----------------------------------------------------------------------------------------
+// Per-bit-width format constants
+// ----------------------------------------------------------------------------------------
+template <int BITS>
+struct Fmt;
+template <>
+struct Fmt<4> {
+    static constexpr int NJ = 4;        // pair fields per 32-bit word == accumulators per tile
+    static constexpr int CPS = 1;       // 128-column TMEM chunks per 64-k stage
+    static constexpr int K2C = 32;      // k-pairs per chunk (TMEM columns per j)
+    static constexpr int ROWS = 128;    // smem rows per stage
+    static constexpr int LUTN = 256;    // table2 entries
+    static constexpr int SCH = 8;       // scale groups per smem scale chunk
+    static constexpr int STAGE_READERS = 4;
+};
+template <>
+struct Fmt<2> {
+    static constexpr int NJ = 8;
+    static constexpr int CPS = 2;
+    static constexpr int K2C = 16;
+    static constexpr int ROWS = 128;
+    static constexpr int LUTN = 16;
+    static constexpr int SCH = 8;
+    static constexpr int STAGE_READERS = 8;
+};
+template <>
+struct Fmt<3> {
+    static constexpr int NJ = 16;
+    static constexpr int CPS = 4;
+    static constexpr int K2C = 8;
+    static constexpr int ROWS = 384;
+    static constexpr int LUTN = 64;
+    static constexpr int SCH = 4;
+    static constexpr int STAGE_READERS = 8;
+};
+
+constexpr int kDequantWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kScaleWarp0 = 10;
+constexpr int kScaleWarps = 2;
+constexpr int kWarps = 12;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxStages = 8;
+constexpr int kMaxChunkSlots = 3;
+constexpr int kTmemCols = 512;
+constexpr int kStageK = 64;
+
+struct SmemCtl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t a_full[kMaxChunkSlots];
+    uint64_t a_empty[kMaxChunkSlots];
+    uint64_t sc_full[2];
+    uint64_t sc_empty[2];
+    uint64_t acc_full;
+    uint64_t acc_empty;
+    uint32_t tmem_base;
+    int is_last;
+};
+
+// ----------------------------------------------------------------------------------------
+// Work partition (identical arithmetic in every role)
+// ----------------------------------------------------------------------------------------
+struct Range {
+    int it0, it1;
+};
+
+__device__ __forceinline__ Range cta_range(const QgemmParams& p, int b, int grid) {
+    Range r;
+    if (p.streamk) {
+        int total = p.n_tiles * p.m_tiles * p.k_iters;
+        int base = total / grid, rem = total - base * grid;
+        r.it0 = b * base + min(b, rem);
+        r.it1 = r.it0 + base + (b < rem ? 1 : 0);
+    } else {
+        int tiles = p.n_tiles * p.m_tiles;
+        int base = tiles / grid, rem = tiles - base * grid;
+        int t0 = b * base + min(b, rem);
+        int t1 = t0 + base + (b < rem ? 1 : 0);
+        r.it0 = t0 * p.k_iters;
+        r.it1 = t1 * p.k_iters;
+    }
+    return r;
+}
+
+__device__ __forceinline__ int streamk_it0_of(const QgemmParams& p, int c, int grid) {
+    int total = p.n_tiles * p.m_tiles * p.k_iters;
+    int base = total / grid, rem = total - base * grid;
+    return c * base + min(c, rem);
+}
+__device__ __forceinline__ int streamk_cta_of(const QgemmParams& p, int it, int grid) {
+    int total = p.n_tiles * p.m_tiles * p.k_iters;
+    int base = total / grid, rem = total - base * grid;
+    int thr = rem * (base + 1);
+    return it < thr ? it / (base + 1) : rem + (it - thr) / base;
+}
+
+// column of N that TMEM lane L / field j of this tile maps to (relative to the tile's first column)
+template <int BITS>
+__device__ __forceinline__ int n_local(int L, int j, int tile_p) {
+    constexpr int NJ = Fmt<BITS>::NJ;
+    if (BITS == 3 || tile_p == 32) return (L >> 5) * (NJ * 32) + j * 32 + (L & 31);
+    return (L >> 6) * (NJ * 64) + j * 64 + (L & 63);
+}
+
+// ----------------------------------------------------------------------------------------
+// Dequantise one 128-column TMEM chunk for lane L:  packed words (smem, 128B-swizzled rows)
+// -> table2 pair lookup (32x lane-replicated LUT: bank == lane, conflict free) -> one
+// mul.{f16,bf16}x2 by the group scale -> tcgen05.st.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lut_ld(uint32_t lut_lane, uint32_t code) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(lut_lane + (code << 7)));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int BITS, bool BF16>
+struct Dequant;
+
+template <bool BF16>
+struct Dequant<4, BF16> {
+    static __device__ __forceinline__ void run(uint32_t wstage, int /*sub*/, int L, uint32_t lut_lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
+        const uint32_t row = wstage + L * 128;
+        const int x = L & 7;
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 v = lds128(row + ((c ^ x) << 4));
+            w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                uint32_t code = (w[i] >> (8 * j)) & 0xffu;
+                r[i] = mul2<BF16>(lut_ld(lut_lane, code), sc[j]);
+            }
+            tmem_st_32x32b_x32(tchunk + j * 32, r);
+        }
+    }
+};
+
+template <bool BF16>
+struct Dequant<2, BF16> {
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
+        const uint32_t row = wstage + L * 128;
+        const int x = L & 7;
+        uint32_t w[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 v = lds128(row + (((4 * sub + c) ^ x) << 4));
+            w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            uint32_t r[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * jj + h;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    uint32_t code = (w[i] >> (4 * j)) & 0xfu;
+                    r[h * 16 + i] = mul2<BF16>(lut_ld(lut_lane, code), sc[j]);
+                }
+            }
+            tmem_st_32x32b_x32(tchunk + jj * 32, r);
+        }
+    }
+};
+
+template <bool BF16>
+struct Dequant<3, BF16> {
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
+        // plane 0 rows [0,128); planes 1/2 rows [128,384): 64 per 32-row block, second plane +32
+        const uint32_t row0 = wstage + L * 128;
+        const uint32_t row1 = wstage + (128 + (L >> 5) * 64 + (L & 31)) * 128;
+        const uint32_t row2 = row1 + 32 * 128;
+        const int x = L & 7;
+        uint32_t w0[8], w1[8], w2[8];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint32_t off = ((2 * sub + c) ^ x) << 4;
+            uint4 a = lds128(row0 + off), b = lds128(row1 + off), d = lds128(row2 + off);
+            w0[4 * c + 0] = a.x; w0[4 * c + 1] = a.y; w0[4 * c + 2] = a.z; w0[4 * c + 3] = a.w;
+            w1[4 * c + 0] = b.x; w1[4 * c + 1] = b.y; w1[4 * c + 2] = b.z; w1[4 * c + 3] = b.w;
+            w2[4 * c + 0] = d.x; w2[4 * c + 1] = d.y; w2[4 * c + 2] = d.z; w2[4 * c + 3] = d.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            uint32_t r[32];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const int j = 4 * jj + h;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t code;
+                    if (j < 15) {
+                        const uint32_t w = (j % 3 == 0) ? w0[i] : (j % 3 == 1) ? w1[i] : w2[i];
+                        code = (w >> (6 * (j / 3))) & 0x3fu;
+                    } else {
+                        code = (w0[i] >> 30) | ((w1[i] >> 30) << 2) | ((w2[i] >> 30) << 4);
+                    }
+                    r[h * 8 + i] = mul2<BF16>(lut_ld(lut_lane, code), sc[j]);
+                }
+            }
+            tmem_st_32x32b_x32(tchunk + jj * 32, r);
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------------------
+// The kernel
+// ----------------------------------------------------------------------------------------
+template <int BITS, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+                   const QgemmParams p) {
+    using F = Fmt<BITS>;
+    constexpr int NJ = F::NJ;
+    constexpr int CPS = F::CPS;
+    constexpr int K2C = F::K2C;
+    constexpr int TN = NJ * 128;
+    constexpr int SCH = F::SCH;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const uint32_t ring = smem_base;
+    const uint32_t lut = ring + p.stages * p.stage_bytes;
+    const uint32_t sc_smem = lut + F::LUTN * 128;
+    uint16_t* sc_gen = reinterpret_cast<uint16_t*>(smem_gen + (sc_smem - smem_base));
+    constexpr uint32_t kScSlotElems = SCH * TN;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_gen + (sc_smem + 2 * kScSlotElems * 2 - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int grid = gridDim.x;
+    const Range rg = cta_range(p, blockIdx.x, grid);
+
+    // ---- one-time setup -------------------------------------------------------------
+    if (warp == kProducerWarp && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_a);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 1);
+            mbar_init(smem_u32(&ctl->empty[s]), F::STAGE_READERS + 1);
+        }
+        for (int c = 0; c < kMaxChunkSlots; ++c) {
+            mbar_init(smem_u32(&ctl->a_full[c]), 4);
+            mbar_init(smem_u32(&ctl->a_empty[c]), 1);
+        }
+        for (int c = 0; c < 2; ++c) {
+            mbar_init(smem_u32(&ctl->sc_full[c]), kScaleWarps);
+            mbar_init(smem_u32(&ctl->sc_empty[c]), kDequantWarps);
+        }
+        mbar_init(smem_u32(&ctl->acc_full), 1);
+        mbar_init(smem_u32(&ctl->acc_empty), kDequantWarps);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+        tmem_relinquish();
+    }
+    {   // lane-replicated LUT: entry e of lane l at lut + e*128 + l*4  (weights-only data: no PDL wait)
+        uint32_t* lut_gen = reinterpret_cast<uint32_t*>(smem_gen + (lut - smem_base));
+        for (int i = threadIdx.x; i < F::LUTN * 32; i += kThreads) lut_gen[i] = __ldg(p.table2 + (i >> 5));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ctl->tmem_base;
+    pdl_launch_dependents();
+
+    const uint32_t acc_col = p.nchunk * 128;   // accumulators sit after the A chunk slots
+
+    if (warp == kProducerWarp) {
+        // =============================== TMA producer ===============================
+        if (lane == 0 && rg.it1 > rg.it0) {
+            const uint64_t pol_w = policy_evict_first();
+            const uint64_t pol_a = policy_evict_last();
+            const int n_it = rg.it1 - rg.it0;
+            const int npro = min(p.stages, n_it);
+            auto coords = [&](int it, int& nt, int& mt, int& k) {
+                int tile = it / p.k_iters;
+                k = it - tile * p.k_iters;
+                nt = tile / p.m_tiles;
+                mt = tile - nt * p.m_tiles;
+            };
+            auto load_w = [&](int it, int s) {
+                int nt, mt, k;
+                coords(it, nt, mt, k);
+                const uint32_t dst = ring + s * p.stage_bytes;
+                const uint32_t bar = smem_u32(&ctl->full[s]);
+                if (BITS == 3) {
+                    tma_load_2d(dst, &tmap_w, bar, k * kStageK, nt * 128, pol_w);
+                    tma_load_2d(dst + 128 * 128, &tmap_w, bar, k * kStageK, p.plane1_row0 + nt * 256, pol_w);
+                    tma_load_2d(dst + 256 * 128, &tmap_w, bar, k * kStageK, p.plane1_row0 + nt * 256 + 128, pol_w);
+                } else {
+                    tma_load_2d(dst, &tmap_w, bar, k * kStageK, nt * 128, pol_w);
+                }
+            };
+            auto load_a = [&](int it, int s) {
+                int nt, mt, k;
+                coords(it, nt, mt, k);
+                tma_load_2d(ring + s * p.stage_bytes + p.w_bytes, &tmap_a, smem_u32(&ctl->full[s]), k * kStageK,
+                            mt * p.mb, pol_a);
+            };
+            // Weights never depend on the previous kernel in the stream: start streaming them
+            // before the programmatic-dependency wait, activations after it.
+            for (int i = 0; i < npro; ++i) {
+                mbar_arrive_expect_tx(smem_u32(&ctl->full[i]), p.w_bytes + p.b_bytes);
+                load_w(rg.it0 + i, i);
+            }
+            pdl_wait_prior_grids();
+            for (int i = 0; i < npro; ++i) load_a(rg.it0 + i, i);
+            int stage = npro % p.stages;
+            uint32_t phase = (npro == p.stages) ? 1u : 0u;
+            for (int i = npro; i < n_it; ++i) {
+                mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u, p.diag, p.timeout_ns, SITE_PROD_EMPTY, stage, i);
+                mbar_arrive_expect_tx(smem_u32(&ctl->full[stage]), p.w_bytes + p.b_bytes);
+                load_w(rg.it0 + i, stage);
+                load_a(rg.it0 + i, stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =============================== MMA issuer =================================
+        if (lane == 0 && rg.it1 > rg.it0) {
+            const uint32_t idesc = make_idesc_f16(BF16, 128, p.mb);
+            int stage = 0;
+            uint32_t phase = 0;
+            int cc = 0;       // chunk counter
+            int seg = 0;
+            for (int it = rg.it0; it < rg.it1;) {
+                const int tile = it / p.k_iters;
+                const int kb = it - tile * p.k_iters;
+                const int ke = min(p.k_iters, kb + (rg.it1 - it));
+                mbar_wait(smem_u32(&ctl->acc_empty), (seg & 1) ^ 1u, p.diag, p.timeout_ns, SITE_MMA_ACCEMPTY, 0, seg);
+                tc_fence_after();
+                for (int k = kb; k < ke; ++k) {
+                    mbar_wait(smem_u32(&ctl->full[stage]), phase, p.diag, p.timeout_ns, SITE_MMA_FULL, stage, it);
+                    const uint64_t bdesc = make_smem_desc_sw128(ring + stage * p.stage_bytes + p.w_bytes);
+#pragma unroll 1
+                    for (int sub = 0; sub < CPS; ++sub, ++cc) {
+                        const int slot = cc % p.nchunk;
+                        const uint32_t apar = (cc / p.nchunk) & 1;
+                        mbar_wait(smem_u32(&ctl->a_full[slot]), apar, p.diag, p.timeout_ns, SITE_MMA_AFULL, slot, cc);
+                        tc_fence_after();
+                        const bool first = (k == kb) && (sub == 0);
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                            for (int kk = 0; kk < K2C / 8; ++kk) {
+                                const uint32_t a_addr = tmem + slot * 128 + j * K2C + kk * 8;
+                                const uint64_t b = bdesc + (uint64_t)((sub * K2C * 4 + kk * 32) >> 4);
+                                tc_mma_ts(tmem + acc_col + j * p.mb, a_addr, b, idesc, (first && kk == 0) ? 0u : 1u);
+                            }
+                        }
+                        tc_commit(smem_u32(&ctl->a_empty[slot]));
+                    }
+                    tc_commit(smem_u32(&ctl->empty[stage]));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(smem_u32(&ctl->acc_full));
+                it += ke - kb;
+                ++seg;
+            }
+        }
+    } else if (warp >= kScaleWarp0) {
+        // =============================== scale loaders ==============================
+        const int tid = (warp - kScaleWarp0) * 32 + lane;
+        int n_sc = 0;
+        const bool vec_ok = ((p.G % SCH) == 0) && ((reinterpret_cast<uintptr_t>(p.S) & 15) == 0);
+        for (int it = rg.it0; it < rg.it1;) {
+            const int tile = it / p.k_iters;
+            const int kb = it - tile * p.k_iters;
+            const int ke = min(p.k_iters, kb + (rg.it1 - it));
+            const int nt = tile / p.m_tiles;
+            const int c_first = (kb * kStageK / p.group_size) / SCH;
+            const int c_last = ((ke * kStageK - 1) / p.group_size) / SCH;
+            for (int c = c_first; c <= c_last; ++c, ++n_sc) {
+                const int slot = n_sc & 1;
+                const uint32_t par = (n_sc >> 1) & 1;
+                mbar_wait(smem_u32(&ctl->sc_empty[slot]), par ^ 1u, p.diag, p.timeout_ns, SITE_SC_EMPTY, slot, n_sc);
+                uint16_t* dst = sc_gen + slot * kScSlotElems;
+                for (int nl = tid; nl < TN; nl += kScaleWarps * 32) {
+                    const int n = nt * TN + nl;
+                    uint16_t v[SCH];
+#pragma unroll
+                    for (int g = 0; g < SCH; ++g) v[g] = 0;
+                    if (n < p.N) {
+                        const uint16_t* src = p.S + (size_t)n * p.G + c * SCH;
+                        if (vec_ok) {
+                            if constexpr (SCH == 8) {
+                                uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+                                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+                                v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+                            } else {
+                                uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
+                                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+                            }
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < SCH; ++g)
+                                if (c * SCH + g < p.G) v[g] = __ldg(src + g);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < SCH; ++g) dst[g * TN + nl] = v[g];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_full[slot]));
+            }
+            it += ke - kb;
+        }
+    } else {
+        // ========================= dequantisers + epilogue ==========================
+        const int group = warp >> 2;            // 0 / 1
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int L = q * 32 + lane;            // TMEM lane == packed row within the tile
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t lut_lane = lut + lane * 4;
+        int it_local = 0;                       // stage counter
+        int n_sc = -1;                          // index of the scale chunk currently held
+        bool sc_held = false;
+        int seg = 0;
+        bool synced = false;
+        int nloc[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) nloc[j] = n_local<BITS>(L, j, p.tile_p);
+
+        for (int it = rg.it0; it < rg.it1;) {
+            const int tile = it / p.k_iters;
+            const int kb = it - tile * p.k_iters;
+            const int ke = min(p.k_iters, kb + (rg.it1 - it));
+            const int nt = tile / p.m_tiles;
+            const int mt = tile - nt * p.m_tiles;
+            int cur_sc = -1;
+            for (int k = kb; k < ke; ++k, ++it_local) {
+                const int stage = it_local % p.stages;
+                const uint32_t sphase = (it_local / p.stages) & 1;
+                // ---- scale chunk bookkeeping (every warp consumes every chunk) ----
+                const int g = (k * kStageK) / p.group_size;
+                const int sc_id = g / SCH;
+                if (sc_id != cur_sc) {
+                    if (sc_held) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[n_sc & 1]));
+                    }
+                    ++n_sc;
+                    sc_held = true;
+                    cur_sc = sc_id;
+                    mbar_wait(smem_u32(&ctl->sc_full[n_sc & 1]), (n_sc >> 1) & 1, p.diag, p.timeout_ns, SITE_DQ_SCALE,
+                              n_sc & 1, n_sc);
+                }
+                bool touched = false;
+#pragma unroll 1
+                for (int sub = 0; sub < CPS; ++sub) {
+                    const int cc = it_local * CPS + sub;
+                    if ((cc & 1) != group) continue;
+                    if (!touched) {
+                        mbar_wait(smem_u32(&ctl->full[stage]), sphase, p.diag, p.timeout_ns, SITE_DQ_FULL, stage, it_local);
+                        touched = true;
+                    }
+                    const int slot = cc % p.nchunk;
+                    const uint32_t apar = (cc / p.nchunk) & 1;
+                    // group scales for this lane's NJ columns, replicated into both halves
+                    uint32_t sc[NJ];
+                    {
+                        const uint16_t* src = sc_gen + (n_sc & 1) * kScSlotElems + (g % SCH) * TN;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            uint32_t s = src[nloc[j]];
+                            sc[j] = s | (s << 16);
+                        }
+                    }
+                    mbar_wait(smem_u32(&ctl->a_empty[slot]), apar ^ 1u, p.diag, p.timeout_ns, SITE_DQ_AEMPTY, slot, cc);
+                    tc_fence_after();
+                    Dequant<BITS, BF16>::run(ring + stage * p.stage_bytes, sub, L, lut_lane, sc,
+                                             tmem + lane_sel + slot * 128);
+                    if (sub + 2 >= CPS) {   // this warp's last read of the stage
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[stage]));
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[slot]));
+                    if (p.dbg != nullptr && blockIdx.x == 0 && cc == 0) {
+                        // debug: read the chunk back out of TMEM (128 lanes x 128 columns)
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            uint32_t r[32];
+                            tmem_ld_32x32b_x32(tmem + lane_sel + slot * 128 + c4 * 32, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) p.dbg[L * 128 + c4 * 32 + i] = r[i];
+                        }
+                    }
+                }
+            }
+            // release the last scale chunk of the segment
+            if (sc_held) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[n_sc & 1]));
+                sc_held = false;
+            }
+
+            // ------------------------------- epilogue ------------------------------------
+            mbar_wait(smem_u32(&ctl->acc_full), seg & 1, p.diag, p.timeout_ns, SITE_DQ_ACCFULL, 0, seg);
+            tc_fence_after();
+            if (!synced) { pdl_wait_prior_grids(); synced = true; }   // D / workspace may be in use by the prior grid
+            const bool full_k = (kb == 0) && (ke == p.k_iters);
+            const int m_base = mt * p.mb;
+            const int n_base = nt * TN;
+            float* part = nullptr;
+            int contributors = 1, first_cta = 0;
+            if (!full_k) {
+                const int tile_it0 = tile * p.k_iters;
+                first_cta = streamk_cta_of(p, tile_it0, grid);
+                contributors = streamk_cta_of(p, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
+                const int which = (tile == rg.it0 / p.k_iters) ? 0 : 1;
+                part = reinterpret_cast<float*>(p.workspace + p.partial_offset) +
+                       (size_t)(2 * blockIdx.x + which) * (NJ * p.mb * 128);
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if ((j & 1) != group) continue;
+                const int n = n_base + nloc[j];
+                for (int mc = 0; mc < p.mb; mc += 16) {
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(tmem + lane_sel + acc_col + j * p.mb + mc, r);
+                    tc_wait_ld();
+                    if (full_k) {
+                        if (n < p.N) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int m = m_base + mc + i;
+                                if (m < p.M) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(__uint_as_float(r[i]));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) part[(j * p.mb + mc + i) * 128 + L] = __uint_as_float(r[i]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
+
+            if (!full_k) {
+                // Deterministic fix-up: every contributor parks its fp32 partial; whoever
+                // arrives last sums them in k order and writes the tile.  No spinning.
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (threadIdx.x == 0) {
+                    int old = atomicAdd(reinterpret_cast<int*>(p.workspace) + tile, 1);
+                    int last = (old == contributors - 1) ? 1 : 0;
+                    if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
+                    __threadfence();
+                    ctl->is_last = last;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (ctl->is_last) {
+                    const float* pbase = reinterpret_cast<const float*>(p.workspace + p.partial_offset);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        if ((j & 1) != group) continue;
+                        const int n = n_base + nloc[j];
+                        if (n >= p.N) continue;
+                        for (int mi = 0; mi < p.mb; ++mi) {
+                            const int m = m_base + mi;
+                            if (m >= p.M) break;
+                            float acc = 0.f;
+                            for (int c = 0; c < contributors; ++c) {
+                                const int cta = first_cta + c;
+                                const int w = (tile == streamk_it0_of(p, cta, grid) / p.k_iters) ? 0 : 1;
+                                acc += __ldcg(pbase + (size_t)(2 * cta + w) * (NJ * p.mb * 128) + (j * p.mb + mi) * 128 + L);
+                            }
+                            p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(acc);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // is_last is reused by the next segment
+            }
+            it += ke - kb;
+            ++seg;
+        }
+    }
+
+    // ---- teardown ------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+static int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return FB_ERR_DRIVER;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? FB_OK : FB_ERR_TENSORMAP;
+}
+
+template <int BITS>
+static void plan_sizes(int mb, uint32_t* w_bytes, uint32_t* b_bytes, uint32_t* stage_bytes, uint32_t* fixed_bytes) {
+    using F = Fmt<BITS>;
+    *w_bytes = F::ROWS * 128;
+    *b_bytes = mb * 128;
+    *stage_bytes = (*w_bytes + *b_bytes + 1023u) & ~1023u;
+    *fixed_bytes = F::LUTN * 128 + 2 * F::SCH * F::NJ * 128 * 2 + sizeof(SmemCtl) + 1024 /*alignment slack*/;
+}
+
+int qgemm_max_mb(int bits) { return bits == 4 ? 64 : bits == 2 ? 32 : 16; }
+
+template <int BITS, bool BF16>
+static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
+    using F = Fmt<BITS>;
+    constexpr int TN = F::NJ * 128;
+    QgemmParams p{};
+    p.S = static_cast<const uint16_t*>(a.S);
+    p.table2 = static_cast<const uint32_t*>(a.table2);
+    p.D = static_cast<uint16_t*>(a.D);
+    p.workspace = static_cast<uint8_t*>(a.workspace);
+    p.diag = a.diag;
+    p.dbg = a.dbg;
+    p.timeout_ns = a.timeout_ns;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.group_size = a.group_size;
+    p.G = a.K / a.group_size;
+    p.tile_p = a.tile_p;
+    int mb_max = qgemm_max_mb(BITS);
+    int mb = ((a.M + 15) / 16) * 16;
+    if (mb > mb_max) mb = mb_max;
+    if (a.force_mb > 0) mb = a.force_mb;
+    p.mb = mb;
+    p.n_tiles = (a.N + TN - 1) / TN;
+    p.m_tiles = (a.M + mb - 1) / mb;
+    p.k_iters = a.K / kStageK;
+    p.nchunk = (kTmemCols - F::NJ * mb) / 128;
+    if (p.nchunk > kMaxChunkSlots) p.nchunk = kMaxChunkSlots;
+    if (p.nchunk < 2) return FB_ERR_INTERNAL;
+    p.plane1_row0 = (BITS == 3) ? a.N / 16 : 0;
+
+    uint32_t fixed;
+    plan_sizes<BITS>(mb, &p.w_bytes, &p.b_bytes, &p.stage_bytes, &fixed);
+    const uint32_t smem_budget = 232448;   // 227 KB
+    int stages = (int)((smem_budget - fixed) / p.stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
+    if (stages < 2) return FB_ERR_INTERNAL;
+    p.stages = stages;
+    const uint32_t smem_bytes = stages * p.stage_bytes + fixed;
+
+    const long long tiles = (long long)p.n_tiles * p.m_tiles;
+    const long long total = tiles * p.k_iters;
+    if (total > 0x3fffffffLL) return FB_ERR_SHAPE;
+    int grid = a.num_sms;
+    if (a.force_grid > 0) grid = a.force_grid;
+    p.streamk = (tiles < 4LL * grid) ? 1 : 0;
+    if (a.force_streamk >= 0) p.streamk = a.force_streamk;
+    if (p.streamk) { if (grid > total) grid = (int)total; }
+    else           { if (grid > tiles) grid = (int)tiles; }
+
+    // workspace: [tile counters][fp32 partials: 2 slots per CTA]
+    const size_t counters = ((size_t)tiles * 4 + 1023) & ~(size_t)1023;
+    p.partial_offset = (uint32_t)counters;
+    if (p.streamk) {
+        const size_t need = counters + (size_t)grid * 2 * F::NJ * mb * 128 * 4;
+        if (counters > 0xffffffffull || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
+    }
+
+    CUtensorMap tm_w, tm_a;
+    const uint64_t P = (uint64_t)a.N / 16 * BITS;
+    int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, kStageK, 128);
+    if (rc != FB_OK) return rc;
+    rc = make_tmap_2d(&tm_a, BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.A,
+                      (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.K * 2, kStageK, (uint32_t)mb);
+    if (rc != FB_OK) return rc;
+
+    auto kern = qgemm_sm100_kernel<BITS, BF16>;
+    static bool attr_set[64] = {};
+    if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
+            cudaGetLastError();
+            return FB_ERR_LAUNCH;
+        }
+        attr_set[a.device] = true;
+    }
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    int nattr = 0;
+    if (a.flags & FB_FLAG_PDL) {
+        attrs[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = nattr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, tm_a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_LAUNCH;
+    }
+    return FB_OK;
+}
+
+int qgemm_launch(const QgemmArgs& a, cudaStream_t stream) {
+    switch (a.num_bits * 2 + (a.bf16 ? 1 : 0)) {
+        case 4 * 2 + 0: return launch_t<4, false>(a, stream);
+        case 4 * 2 + 1: return launch_t<4, true>(a, stream);
+        case 2 * 2 + 0: return launch_t<2, false>(a, stream);
+        case 2 * 2 + 1: return launch_t<2, true>(a, stream);
+        case 3 * 2 + 0: return launch_t<3, false>(a, stream);
+        case 3 * 2 + 1: return launch_t<3, true>(a, stream);
+    }
+    return FB_ERR_BITS;
+}
+
+}  // namespace fb

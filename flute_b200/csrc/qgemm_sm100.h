@@ -1,0 +1,62 @@
+// Internal host <-> kernel interface of the sm_100a LUT-qGEMM (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/flute_b200.h"
+
+namespace fb {
+
+struct Diag;
+
+enum : int { FB_FLAG_PDL = 1 };
+
+// Arguments as the C ABI receives them, plus test-only overrides (0 / -1 = engine's choice).
+struct QgemmArgs {
+    const void* A;
+    const void* Q;
+    void* D;
+    const void* S;
+    const void* table2;
+    void* workspace;
+    size_t workspace_bytes;
+    int M, N, K;
+    int num_bits, group_size, tile_p;
+    int bf16;
+    int flags;
+    int device;
+    int num_sms;
+    Diag* diag;
+    uint32_t* dbg;
+    uint64_t timeout_ns;
+    int force_mb;
+    int force_stages;
+    int force_grid;
+    int force_streamk;
+};
+
+// Kernel parameters (passed by value).
+struct QgemmParams {
+    const uint16_t* S;        // [N, G] T
+    const uint32_t* table2;   // [4^bits] packed T pairs
+    uint16_t* D;              // [M, N] T
+    uint8_t* workspace;       // [tile counters | fp32 partials]
+    Diag* diag;
+    uint32_t* dbg;
+    uint64_t timeout_ns;
+    int M, N, K, G;
+    int group_size, tile_p;
+    int mb;                   // activation rows per tile == MMA N
+    int n_tiles, m_tiles, k_iters;
+    int stages, nchunk, streamk;
+    uint32_t partial_offset;
+    uint32_t stage_bytes, w_bytes, b_bytes;
+    uint32_t plane1_row0;     // 3-bit: first row of planes 1/2 (N/16)
+};
+
+int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);
+int qgemm_max_mb(int bits);
+
+}  // namespace fb

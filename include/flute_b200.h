@@ -1,0 +1,138 @@
+/*
+ * flute_b200 -- C ABI of the B200 (sm_100a) LUT-quantized GEMM engine.
+ *
+ * This is the drop-in boundary for the reference's `flute/csrc`: plain pointers and sizes,
+ * no torch types.  Every device pointer is a CUDA device pointer on `device`; `stream` is a
+ * cudaStream_t passed as void*.  All calls are asynchronous on `stream`, allocate nothing,
+ * never synchronise, and are CUDA-graph capturable.  Return value: 0 (FLUTE_B200_OK) or a
+ * negative FLUTE_B200_ERR_* code; `flute_b200_last_error()` gives the message for the calling
+ * thread.  Citations are into the reference tree (HanGuo97/flute @ v0.4.2).
+ */
+#ifndef FLUTE_B200_H_
+#define FLUTE_B200_H_
+
+#if defined(__GNUC__)
+#define FLUTE_B200_API __attribute__((visibility("default")))
+#else
+#define FLUTE_B200_API
+#endif
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUTE_B200_VERSION 100 /* 0.1.0 */
+
+/* dtype codes: the arithmetic type T of activations, scales, tables and outputs */
+#define FLUTE_B200_F16 0
+#define FLUTE_B200_BF16 1
+
+/* flags */
+#define FLUTE_B200_FLAG_PDL 1 /* launch with programmatic stream serialization (overlap with the previous kernel) */
+
+/* error codes (the reference raises AT_ERROR / launch-check failures, flute/csrc/qgemm.cpp:82,153,171) */
+enum {
+    FB_OK = 0,
+    FB_ERR_BITS = -1,      /* num_bits not in {2,3,4}            (qgemm.cpp:171) */
+    FB_ERR_GROUP = -2,     /* group_size not in {64,128,256}     (qgemm.cpp:153) */
+    FB_ERR_DTYPE = -3,     /* dtype not fp16/bf16                (qgemm.cpp:176-193) */
+    FB_ERR_SHAPE = -4,     /* K % 64, K % group, N % block, M < 0 ... (ops.py:17-49) */
+    FB_ERR_TILE_P = -5,    /* tile_P not 32/64, or 64 with 3-bit (utils.py:138-139) */
+    FB_ERR_WORKSPACE = -6, /* workspace too small for the Stream-K partials */
+    FB_ERR_LAUNCH = -7,    /* CUDA launch failure                (qgemm.cpp:82) */
+    FB_ERR_DRIVER = -8,    /* cuTensorMapEncodeTiled unavailable */
+    FB_ERR_TENSORMAP = -9, /* tensor-map encode rejected (misaligned pointer / stride) */
+    FB_ERR_NULL = -10,     /* null pointer */
+    FB_ERR_DEVICE = -11,   /* not an sm_100 device / cudaSetDevice failed */
+    FB_ERR_INTERNAL = -12,
+    FB_ERR_HADAMARD = -13, /* hadamard size not a power of two <= 32768 (hadamard_transform.cpp:24-26) */
+    FB_ERR_KERNEL = -14    /* a previous kernel trapped; see flute_b200_last_error() */
+};
+#define FLUTE_B200_OK FB_OK
+
+/*
+ * D[M,N] = A[M,K] . W_hat[K,N],  W_hat[k,n] = round_T(table2[code].{lo,hi} * S[n, k / group_size]).
+ *
+ * Replaces  torch.ops.flute.qgemm_raw_simple -> qgemm_raw<T,NumBits,GroupSize> -> _qgemm_raw -> qgemm_host
+ *           (flute/csrc/qgemm.cpp:44-198, qgemm_kernel_raw_generated.cu:15-768, qgemm_kernel.hpp:841-939).
+ *   A         [M, K]  T, row-major, contiguous                      (qgemm.cpp:71,110)
+ *   Q         [N/16*num_bits, K] int16, the reference's packed wire format (flute/utils.py:59-253), tile_P as packed
+ *   D         [M, N]  T, row-major (output)
+ *   S         [N, K/group_size] T                                   (qgemm_kernel.hpp:137)
+ *   table     [2^num_bits] T -- accepted for signature parity; like every instantiated reference
+ *             template (codegen_utils.py:97-102) the kernel looks up through table2 only
+ *   table2    [2^num_bits, 2^num_bits, 1] float32 = bit view of T pairs, low half = even k (flute/utils.py:15-33)
+ *   workspace zero-initialised once by the caller, reused across calls on one stream; the kernel
+ *             leaves every flag it touches zero again (contract of flute/utils.py:36-56)
+ *   tile_P    32 or 64: the packing the weights were stored with (TEMPLATE_CONFIGS[(bits,id)]["TileP"])
+ *   dtype     FLUTE_B200_F16 / FLUTE_B200_BF16
+ */
+FLUTE_B200_API int flute_b200_qgemm(const void* A, const void* Q, void* D, const void* S, const void* table, const void* table2,
+                     void* workspace, size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size,
+                     int tile_P, int dtype, int flags, int device, void* stream);
+
+/*
+ * Same computation with HOST activation / output buffers: copies A host->device into
+ * `A_dev_scratch`, runs the GEMM, copies D device->host, all on `stream` (pinned host memory makes
+ * the copies asynchronous).  Weights, scales, tables and workspace stay device-resident, as they
+ * do behind `FluteLinear.forward` (flute/integrations/base.py:277-301).  This is the call
+ * bench.py times for its end-to-end number.
+ */
+FLUTE_B200_API int flute_b200_qgemm_host(const void* A_host, void* D_host, void* A_dev_scratch, void* D_dev_scratch, const void* Q,
+                          const void* S, const void* table, const void* table2, void* workspace,
+                          size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size, int tile_P,
+                          int dtype, int flags, int device, void* stream);
+
+/*
+ * out = in.reshape(rows, had_size) @ H / sqrt(had_size)  (Sylvester order), T in, T out, fp32 inside.
+ * Replaces hadamard_transform(Tensor&, bool) (flute/csrc/hadamard_transform.cpp:17-57,
+ * hadamard_transform_cuda.cu:92-748) as used by qgemm_raw_simple_hadamard (qgemm.cpp:201-244).
+ * `in` may equal `out`.
+ */
+FLUTE_B200_API int flute_b200_hadamard(const void* in, void* out, long rows, int had_size, int dtype, int device, void* stream);
+
+/*
+ * W_hat[K, N] (T, row-major) from the packed weights: the dequantiser alone.  Replaces the
+ * identity-matrix GEMM the reference uses to reconstruct / unpack weights
+ * (flute/utils.py:347-407): same values, no K x K identity operand.
+ */
+FLUTE_B200_API int flute_b200_dequantize(const void* Q, const void* S, const void* table2, void* W_hat, int N, int K, int num_bits,
+                          int group_size, int tile_P, int dtype, int device, void* stream);
+
+/* Bytes of workspace `make_workspace_streamk` should allocate (flute/utils.py:36-45 formula). */
+FLUTE_B200_API size_t flute_b200_workspace_bytes(int num_sms);
+
+/* SM count of `device` (flute/utils.py:410-412), or a negative error code. */
+FLUTE_B200_API int flute_b200_num_sms(int device);
+
+/* Largest activation-row tile (MMA N) the engine uses for `num_bits`; informational. */
+FLUTE_B200_API int flute_b200_max_batch_tile(int num_bits);
+
+FLUTE_B200_API const char* flute_b200_last_error(void);
+FLUTE_B200_API const char* flute_b200_error_string(int code);
+FLUTE_B200_API int flute_b200_version(void);
+
+/*
+ * Diagnostics.  The kernels bound every barrier wait (default 10 s; 0 disables) and trap with a
+ * reason instead of hanging the GPU.  `flute_b200_set_timeout_ms` changes the bound for later
+ * launches; `flute_b200_check(device)` returns FB_ERR_KERNEL and fills last_error if a kernel on
+ * that device recorded a timeout since the last check.
+ */
+FLUTE_B200_API void flute_b200_set_timeout_ms(long ms);
+FLUTE_B200_API int flute_b200_check(int device);
+
+/* Test hook: like flute_b200_qgemm with explicit tiling overrides (0 / -1 = engine's choice) and an
+ * optional device buffer receiving the first dequantised TMEM chunk (128 x 128 uint32). */
+FLUTE_B200_API int flute_b200_qgemm_debug(const void* A, const void* Q, void* D, const void* S, const void* table2, void* workspace,
+                           size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size, int tile_P,
+                           int dtype, int flags, int device, void* stream, int force_mb, int force_stages,
+                           int force_grid, int force_streamk, void* dbg_chunk);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FLUTE_B200_H_ */
