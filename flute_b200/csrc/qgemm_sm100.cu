@@ -730,12 +730,14 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
 
-    // workspace: [tile counters][fp32 partials: 2 slots per CTA]
-    const size_t counters = ((size_t)tiles * 4 + 1023) & ~(size_t)1023;
-    p.partial_offset = (uint32_t)counters;
+    // workspace: [tile counters: fixed 64 KB][fp32 partials: 2 slots per CTA].  The counter region has a
+    // fixed size so that partials of one call can never alias counters of a later, larger call; counters
+    // are zero on entry (caller zero-initialises once) and every kernel leaves them zero again.
+    constexpr size_t kCounterBytes = 65536;
+    p.partial_offset = (uint32_t)kCounterBytes;
     if (p.streamk) {
-        const size_t need = counters + (size_t)grid * 2 * F::NJ * mb * 128 * 4;
-        if (counters > 0xffffffffull || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
+        const size_t need = kCounterBytes + (size_t)grid * 2 * F::NJ * mb * 128 * 4;
+        if ((size_t)tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
     }
 
     CUtensorMap tm_w, tm_a;

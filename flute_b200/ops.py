@@ -20,6 +20,13 @@ _SCHEMA_QGEMM_HADAMARD = (
     "(Tensor input, Tensor weight, Tensor scales, Tensor table, Tensor table2, Tensor(a!) workspace, "
     "int num_bits, int group_size, int hadamard_size, int template_id, int num_sms) -> Tensor")
 
+import os
+
+# Programmatic dependent launch: the kernel starts streaming WEIGHTS while the previous kernel in the
+# stream drains, and waits (griddepcontrol.wait) before it touches activations, outputs or workspace.
+# Safe next to arbitrary neighbours: kernels launched without the attribute serialise as usual.
+LAUNCH_FLAGS = _lib.FLAG_PDL if os.environ.get("FLUTE_B200_PDL", "1") != "0" else 0
+
 NAMESPACE = "flute"
 try:
     torch.library.define(f"{NAMESPACE}::qgemm_raw_simple", _SCHEMA_QGEMM)
@@ -91,7 +98,7 @@ def _qgemm_cuda(input, weight, scales, table, table2, workspace, num_bits, group
         rc = _lib.lib.flute_b200_qgemm(
             x.data_ptr(), weight.data_ptr(), out.data_ptr(), scales.data_ptr(), table.data_ptr(), table2.data_ptr(),
             workspace.data_ptr(), workspace.numel(), M, N, K, num_bits, group_size,
-            tile_p_of(num_bits, template_id), _dtype_code(input.dtype), 0, dev, stream)
+            tile_p_of(num_bits, template_id), _dtype_code(input.dtype), LAUNCH_FLAGS, dev, stream)
         _lib.check(rc)
     return out.reshape(input.shape[:-1] + (N,))
 

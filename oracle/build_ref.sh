@@ -27,12 +27,13 @@ PY
 mkdir -p "$OUT"
 cat > "$OUT/probe.cu" <<'CU'
 #include "qgemm_kernel.hpp"
-template void qgemm_host<cute::half_t, cute::uint16_t, __half2, cute::Int<108>, cute::Int<128>,
-    cute::Int<16>, cute::Int<64>, cute::Int<32>, cute::Int<3>, cute::Int<4>, cute::Int<64>,
-    config::QuantMapModeEnum::Vectorized, config::AccumulationModeEnum::Mixed,
-    config::DecompositionModeEnum::StreamK, cute::Int<2>, cute::Int<1>>(
-    int, int, int, int, const cute::half_t*, const cute::uint16_t*, cute::half_t*, const cute::half_t*,
-    const cute::half_t*, const __half2*, void*, const int, cudaStream_t);
+// one template of the reference's zoo: 128 threads, TileM16 x TileK64 x TileP32, 3 stages, W4G64, fp16
+template void qgemm_host<cute::half_t, cute::uint16_t, __half2, cute::Int<128>, cute::Int<16>, cute::Int<64>,
+    cute::Int<32>, cute::Int<3>, cute::Int<4>, cute::Int<64>, config::QuantMapModeEnum::Vectorized,
+    config::AccumulationModeEnum::Mixed, config::DecompositionModeEnum::StreamK, cute::Int<2>, cute::Int<1>>(
+    int, int, int, int, const cute::half_t* const, const cute::uint16_t* const, cute::half_t*,
+    const cute::half_t* const, const cute::half_t* const, const __half2* const, void*, const int,
+    const cudaStream_t);
 CU
 if nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr \
      -I"$REF/flute/csrc" -I"$CUTLASS_INC" -c "$OUT/probe.cu" -o "$OUT/probe.o" 2> "$OUT/probe.log"; then

@@ -1,0 +1,107 @@
+"""Per-shape micro-benchmark of the qgemm kernel (not the judged bench; a tuning tool).
+
+For each (N, K, M): enough distinct weight copies to exceed L2 several times are cycled inside one
+CUDA graph, timed with CUDA events; prints achieved GB/s (algorithmic bytes) and TFLOP/s.
+
+    python tools/microbench.py --M 1,16 --shapes llama8b [--bits 4] [--dtype bf16] [--pdl 1]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SHAPE_SETS = {
+    "llama8b": [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)],
+    "llama70b": [(10240, 8192), (8192, 8192), (57344, 8192), (8192, 28672)],
+    "small": [(4096, 4096)],
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--M", default="1")
+    ap.add_argument("--shapes", default="llama8b")
+    ap.add_argument("--bits", type=int, default=4)
+    ap.add_argument("--group", type=int, default=64)
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--force-mb", type=int, default=0)
+    ap.add_argument("--force-stages", type=int, default=0)
+    ap.add_argument("--force-grid", type=int, default=0)
+    ap.add_argument("--force-streamk", type=int, default=-1)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+
+    import torch
+    from flute_b200 import _lib, utils
+    dev = torch.device("cuda", 0)
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    ws = utils.get_workspace_streamk(dev)
+    bits, group = args.bits, args.group
+    table = torch.randn(2 ** bits, device=dev).to(dt)
+    table2 = utils.make_qmap2_from_qmap(table)
+    results = []
+    for (N, K) in SHAPE_SETS[args.shapes]:
+        for M in [int(m) for m in args.M.split(",")]:
+            wbytes = N * K * bits // 8 + N * (K // group) * 2
+            abytes = wbytes + M * K * 2 + M * N * 2 + (2 ** bits) * 2 + (4 ** bits) * 4
+            ncopies = max(2, min(64, (600 * 2 ** 20 + wbytes - 1) // wbytes))
+            Qs = [torch.randint(-32768, 32768, (N // 16 * bits, K), dtype=torch.int16, device=dev) for _ in range(ncopies)]
+            Ss = [(torch.randn((N, K // group), device=dev) / K ** 0.5).to(dt) for _ in range(ncopies)]
+            A = (torch.randn((M, K), device=dev)).to(dt)
+            D = torch.empty((M, N), dtype=dt, device=dev)
+            flags = _lib.FLAG_PDL if args.pdl else 0
+
+            def launch(i):
+                rc = _lib.lib.flute_b200_qgemm_debug(
+                    A.data_ptr(), Qs[i].data_ptr(), D.data_ptr(), Ss[i].data_ptr(), table2.data_ptr(), ws.data_ptr(),
+                    ws.numel(), M, N, K, bits, group, 32, 1 if dt == torch.bfloat16 else 0, flags, 0,
+                    torch.cuda.current_stream().cuda_stream, args.force_mb, args.force_stages, args.force_grid,
+                    args.force_streamk, None)
+                _lib.check(rc)
+
+            for i in range(ncopies):
+                launch(i)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    for i in range(ncopies):
+                        launch(i)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (args.reps * ncopies)
+            gbs = abytes / us / 1e3
+            tfl = 2.0 * M * N * K / us / 1e6
+            _lib.check(_lib.lib.flute_b200_check(0))
+            r = dict(N=N, K=K, M=M, bits=bits, us=us, gbs=gbs, hbm_frac=gbs / peaks["hbm_gbs"], tflops=tfl,
+                     tc_frac=tfl / peaks["bf16_tflops"], copies=ncopies)
+            results.append(r)
+            print(f"N={N:6d} K={K:6d} M={M:5d} W{bits}: {us:9.2f} us  {gbs:8.1f} GB/s ({100 * r['hbm_frac']:5.1f}% HBM)  "
+                  f"{tfl:8.1f} TFLOP/s ({100 * r['tc_frac']:5.1f}% TC)  copies={ncopies}", flush=True)
+            del Qs, Ss
+            torch.cuda.empty_cache()
+    if args.json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
+        with open(args.json, "w") as f:
+            json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
