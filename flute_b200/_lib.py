@@ -27,6 +27,7 @@ EXPORTS = (
     "flute_b200_set_timeout_ms",
     "flute_b200_check",
     "flute_b200_qgemm_debug",
+    "flute_b200_set_trace_buffer",
 )
 
 F16, BF16 = 0, 1
@@ -38,7 +39,7 @@ _vp, _i, _sz, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_long
 def _load() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m flute_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python flute_b200/build.py` "
             "(or __graft_entry__.build()). flute_b200 has no CPU or PyTorch fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     lib.flute_b200_qgemm.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
@@ -67,6 +68,8 @@ def _load() -> ctypes.CDLL:
     lib.flute_b200_version.restype = _i
     lib.flute_b200_set_timeout_ms.argtypes = [_l]
     lib.flute_b200_set_timeout_ms.restype = None
+    lib.flute_b200_set_trace_buffer.argtypes = [_vp]
+    lib.flute_b200_set_trace_buffer.restype = None
     lib.flute_b200_check.argtypes = [_i]
     lib.flute_b200_check.restype = _i
     return lib

@@ -1,6 +1,6 @@
 """Builds flute_b200/libflute_b200.so (the C-ABI library) with nvcc for sm_100a, in-tree.
 
-    python -m flute_b200.build [--force] [--verbose]
+    python flute_b200/build.py [--force] [--verbose]
 
 No torch headers are involved: the library is plain CUDA C++ behind include/flute_b200.h.
 """

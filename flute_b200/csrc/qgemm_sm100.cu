@@ -150,6 +150,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
 template <int BITS, bool BF16>
 struct Dequant;
 
@@ -302,15 +311,21 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
         tmem_relinquish();
     }
-    {   // lane-replicated LUT: entry e of lane l at lut + e*128 + l*4  (weights-only data: no PDL wait)
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 0] = globaltimer_ns();
+    {   // lane-replicated LUT: entry e of lane l at lut + e*128 + l*4  (weights-only data: no PDL wait).
+        // One global load per entry, staged through the (still unused) scale buffer, then replicated.
+        uint32_t* stage = reinterpret_cast<uint32_t*>(sc_gen);
+        for (int i = threadIdx.x; i < F::LUTN; i += kThreads) stage[i] = __ldg(p.table2 + i);
+        __syncthreads();
         uint32_t* lut_gen = reinterpret_cast<uint32_t*>(smem_gen + (lut - smem_base));
-        for (int i = threadIdx.x; i < F::LUTN * 32; i += kThreads) lut_gen[i] = __ldg(p.table2 + (i >> 5));
+        for (int i = threadIdx.x; i < F::LUTN * 32; i += kThreads) lut_gen[i] = stage[i >> 5];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
     pdl_launch_dependents();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 1] = globaltimer_ns();
 
     const uint32_t acc_col = p.nchunk * 128;   // accumulators sit after the A chunk slots
 
@@ -380,6 +395,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 tc_fence_after();
                 for (int k = kb; k < ke; ++k) {
                     mbar_wait(smem_u32(&ctl->full[stage]), phase, p.diag, p.timeout_ns, SITE_MMA_FULL, stage, it);
+                    if (p.trace != nullptr && cc == 0) p.trace[blockIdx.x * 8 + 2] = globaltimer_ns();
                     const uint64_t bdesc = make_smem_desc_sw128(ring + stage * p.stage_bytes + p.w_bytes);
 #pragma unroll 1
                     for (int sub = 0; sub < CPS; ++sub, ++cc) {
@@ -403,6 +419,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
                 tc_commit(smem_u32(&ctl->acc_full));
+                if (p.trace != nullptr) p.trace[blockIdx.x * 8 + 3] = globaltimer_ns();
                 it += ke - kb;
                 ++seg;
             }
@@ -549,80 +566,75 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             // ------------------------------- epilogue ------------------------------------
             mbar_wait(smem_u32(&ctl->acc_full), seg & 1, p.diag, p.timeout_ns, SITE_DQ_ACCFULL, 0, seg);
             tc_fence_after();
+            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 8 + 4] = globaltimer_ns();
             if (!synced) { pdl_wait_prior_grids(); synced = true; }   // D / workspace may be in use by the prior grid
             const bool full_k = (kb == 0) && (ke == p.k_iters);
             const int m_base = mt * p.mb;
             const int n_base = nt * TN;
-            float* part = nullptr;
-            int contributors = 1, first_cta = 0;
+            const int rows_valid = min(p.mb, p.M - m_base);
+            float* accum = nullptr;
+            int contributors = 1;
             if (!full_k) {
+                // Partial K range: accumulate into the tile's fp32 scratch (zero on entry, left zero on exit)
+                // with fire-and-forget reductions; the CTA that arrives last converts and writes the tile.
                 const int tile_it0 = tile * p.k_iters;
-                first_cta = streamk_cta_of(p, tile_it0, grid);
+                const int first_cta = streamk_cta_of(p, tile_it0, grid);
                 contributors = streamk_cta_of(p, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
-                const int which = (tile == rg.it0 / p.k_iters) ? 0 : 1;
-                part = reinterpret_cast<float*>(p.workspace + p.partial_offset) +
-                       (size_t)(2 * blockIdx.x + which) * (NJ * p.mb * 128);
+                accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * p.mb * 128);
             }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 if ((j & 1) != group) continue;
                 const int n = n_base + nloc[j];
-                for (int mc = 0; mc < p.mb; mc += 16) {
+                for (int mc = 0; mc < rows_valid; mc += 16) {
                     uint32_t r[16];
                     tmem_ld_32x32b_x16(tmem + lane_sel + acc_col + j * p.mb + mc, r);
                     tc_wait_ld();
                     if (full_k) {
                         if (n < p.N) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const int m = m_base + mc + i;
-                                if (m < p.M) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(__uint_as_float(r[i]));
-                            }
+                            for (int i = 0; i < 16; ++i)
+                                if (mc + i < rows_valid)
+                                    p.D[(size_t)(m_base + mc + i) * p.N + n] = f32_to_t<BF16>(__uint_as_float(r[i]));
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) part[(j * p.mb + mc + i) * 128 + L] = __uint_as_float(r[i]);
+                        for (int i = 0; i < 16; ++i)
+                            if (mc + i < rows_valid) red_add_f32(accum + (j * p.mb + mc + i) * 128 + L, __uint_as_float(r[i]));
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
+            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 8 + 5] = globaltimer_ns();
 
             if (!full_k) {
-                // Deterministic fix-up: every contributor parks its fp32 partial; whoever
-                // arrives last sums them in k order and writes the tile.  No spinning.
-                __threadfence();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (threadIdx.x == 0) {
-                    int old = atomicAdd(reinterpret_cast<int*>(p.workspace) + tile, 1);
-                    int last = (old == contributors - 1) ? 1 : 0;
+                    // release: publishes this CTA's reductions (cumulative through the barrier above);
+                    // acquire: the last arriver sees everyone else's.
+                    const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
+                    const int last = (old == contributors - 1) ? 1 : 0;
                     if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
-                    __threadfence();
                     ctl->is_last = last;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (ctl->is_last) {
-                    const float* pbase = reinterpret_cast<const float*>(p.workspace + p.partial_offset);
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
                         if ((j & 1) != group) continue;
                         const int n = n_base + nloc[j];
-                        if (n >= p.N) continue;
-                        for (int mi = 0; mi < p.mb; ++mi) {
-                            const int m = m_base + mi;
-                            if (m >= p.M) break;
-                            float acc = 0.f;
-                            for (int c = 0; c < contributors; ++c) {
-                                const int cta = first_cta + c;
-                                const int w = (tile == streamk_it0_of(p, cta, grid) / p.k_iters) ? 0 : 1;
-                                acc += __ldcg(pbase + (size_t)(2 * cta + w) * (NJ * p.mb * 128) + (j * p.mb + mi) * 128 + L);
-                            }
-                            p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(acc);
+                        for (int mi = 0; mi < rows_valid; ++mi) {
+                            float* src = accum + (j * p.mb + mi) * 128 + L;
+                            const float v = __ldcg(src);
+                            *src = 0.f;
+                            if (n < p.N) p.D[(size_t)(m_base + mi) * p.N + n] = f32_to_t<BF16>(v);
                         }
                     }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // is_last is reused by the next segment
+                if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 8 + 6] = globaltimer_ns();
             }
             it += ke - kb;
             ++seg;
@@ -632,6 +644,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     // ---- teardown ------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 7] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, kTmemCols);
@@ -692,6 +705,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.workspace = static_cast<uint8_t*>(a.workspace);
     p.diag = a.diag;
     p.dbg = a.dbg;
+    p.trace = a.trace;
     p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.group_size = a.group_size;
@@ -730,13 +744,13 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
 
-    // workspace: [tile counters: fixed 64 KB][fp32 partials: 2 slots per CTA].  The counter region has a
-    // fixed size so that partials of one call can never alias counters of a later, larger call; counters
-    // are zero on entry (caller zero-initialises once) and every kernel leaves them zero again.
+    // workspace: [tile counters: fixed 64 KB][fp32 tile accumulators, one per output tile].  Both regions are
+    // zero on entry (the caller zero-initialises the workspace once) and every kernel leaves what it touched
+    // zero again, so calls of any shape can follow each other on a stream (contract of flute/utils.py:36-56).
     constexpr size_t kCounterBytes = 65536;
     p.partial_offset = (uint32_t)kCounterBytes;
     if (p.streamk) {
-        const size_t need = kCounterBytes + (size_t)grid * 2 * F::NJ * mb * 128 * 4;
+        const size_t need = kCounterBytes + (size_t)tiles * F::NJ * mb * 128 * 4;
         if ((size_t)tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
     }
 

@@ -30,6 +30,7 @@ struct QgemmArgs {
     int num_sms;
     Diag* diag;
     uint32_t* dbg;
+    unsigned long long* trace;
     uint64_t timeout_ns;
     int force_mb;
     int force_stages;
@@ -45,6 +46,7 @@ struct QgemmParams {
     uint8_t* workspace;       // [tile counters | fp32 partials]
     Diag* diag;
     uint32_t* dbg;
+    unsigned long long* trace;   // optional [grid][8] globaltimer stamps
     uint64_t timeout_ns;
     int M, N, K, G;
     int group_size, tile_p;

@@ -124,6 +124,11 @@ FLUTE_B200_API int flute_b200_version(void);
 FLUTE_B200_API void flute_b200_set_timeout_ms(long ms);
 FLUTE_B200_API int flute_b200_check(int device);
 
+/* Test hook: when non-null, every CTA of later qgemm launches writes 8 globaltimer stamps (ns) to
+ * device_ptr[blockIdx * 8 + i]: start, setup done, first tile landed, last MMA issued, accumulators
+ * complete, epilogue done, fix-up done, exit.  Pass NULL to switch tracing off. */
+FLUTE_B200_API void flute_b200_set_trace_buffer(void* device_ptr);
+
 /* Test hook: like flute_b200_qgemm with explicit tiling overrides (0 / -1 = engine's choice) and an
  * optional device buffer receiving the first dequantised TMEM chunk (128 x 128 uint32). */
 FLUTE_B200_API int flute_b200_qgemm_debug(const void* A, const void* Q, void* D, const void* S, const void* table2, void* workspace,

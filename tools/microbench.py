@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--force-grid", type=int, default=0)
     ap.add_argument("--force-streamk", type=int, default=-1)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--trace", type=int, default=0, help="print a per-CTA timeline of one isolated launch")
     args = ap.parse_args()
 
     import torch
@@ -70,6 +71,22 @@ def main():
             for i in range(ncopies):
                 launch(i)
             torch.cuda.synchronize()
+            if args.trace:
+                tr = torch.zeros((256, 8), dtype=torch.int64, device=dev)
+                _lib.lib.flute_b200_set_trace_buffer(tr.data_ptr())
+                launch(1 % ncopies)
+                torch.cuda.synchronize()
+                _lib.lib.flute_b200_set_trace_buffer(None)
+                t = tr.cpu().numpy()
+                t = t[t[:, 0] > 0]
+                t0 = t[:, 0].min()
+                names = ["start", "setup", "1st-tile", "mma-issued", "acc-full", "epilogue", "fixup", "exit"]
+                import numpy as np
+                print(f"   trace N={N} K={K} M={M}: {t.shape[0]} CTAs; columns = ns since first CTA start (min / median / max)")
+                for c, nm in enumerate(names):
+                    col = t[:, c]; col = col[col > 0] - t0
+                    if col.size:
+                        print(f"     {nm:10s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}   (n={col.size})")
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
             with torch.cuda.stream(side):
