@@ -28,6 +28,7 @@ EXPORTS = (
     "flute_b200_check",
     "flute_b200_qgemm_debug",
     "flute_b200_set_trace_buffer",
+    "flute_b200_set_variant",
 )
 
 F16, BF16 = 0, 1
@@ -68,6 +69,8 @@ def _load() -> ctypes.CDLL:
     lib.flute_b200_version.restype = _i
     lib.flute_b200_set_timeout_ms.argtypes = [_l]
     lib.flute_b200_set_timeout_ms.restype = None
+    lib.flute_b200_set_variant.argtypes = [_i]
+    lib.flute_b200_set_variant.restype = None
     lib.flute_b200_set_trace_buffer.argtypes = [_vp]
     lib.flute_b200_set_trace_buffer.restype = None
     lib.flute_b200_check.argtypes = [_i]

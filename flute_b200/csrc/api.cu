@@ -33,7 +33,8 @@ struct DeviceState {
 };
 DeviceState g_dev[kMaxDevices];
 long g_timeout_ms = 10000;
-unsigned long long* g_trace = nullptr;   // test hook: per-CTA globaltimer stamps
+unsigned long long* g_trace = nullptr;
+int g_variant = -1;                       // test hook: kernel footprint override   // test hook: per-CTA globaltimer stamps
 
 struct DeviceGuard {
     int prev = -1;
@@ -130,6 +131,7 @@ int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* 
     a.diag = diag_for(device, static_cast<cudaStream_t>(stream));
     a.dbg = static_cast<uint32_t*>(dbg);
     a.trace = g_trace;
+    a.variant = g_variant;
     a.timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
     a.force_mb = force_mb; a.force_stages = force_stages; a.force_grid = force_grid; a.force_streamk = force_streamk;
     rc = fb::qgemm_launch(a, static_cast<cudaStream_t>(stream));
@@ -269,6 +271,8 @@ const char* flute_b200_error_string(int code) {
 int flute_b200_version(void) { return FLUTE_B200_VERSION; }
 
 void flute_b200_set_timeout_ms(long ms) { g_timeout_ms = ms; }
+
+void flute_b200_set_variant(int variant) { g_variant = variant; }
 
 void flute_b200_set_trace_buffer(void* device_ptr) { g_trace = static_cast<unsigned long long*>(device_ptr); }
 

@@ -15,11 +15,18 @@
 // it loads: field j of word (L, k2) is dequantised into column k2 of "A_j".  The N
 // permutation the wire format bakes in is undone for free in the epilogue's store address.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over a contiguous Stream-K range):
+// Warp roles (384 threads, persistent over a contiguous Stream-K range):
 //   warps 0-7   dequantisers (two groups of four; warp%4 = TMEM lane quarter) + epilogue
 //   warp  8     TMA producer (packed-weight tiles + activation tiles, mbarrier ring)
-//   warp  9     tcgen05.mma issuer, TMEM allocator
+//   warp  9     tcgen05.mma issuer (warp-uniform loop, one elected lane issues), TMEM allocator
 //   warps 10-11 scale loaders (global -> smem, group-major so reads are conflict-free)
+//
+// Two footprints of the same kernel:
+//   LARGE  1 CTA/SM, 512 TMEM columns, up to 8 stages, Mb up to 64      (M > 16, and 3-bit)
+//   SMALL  2 CTAs/SM, 256 TMEM columns, 3 stages, Mb = 16                (decode, M <= 16)
+// SMALL leaves half of every SM free so that, with programmatic dependent launch, the NEXT
+// kernel in the stream is already resident and has its first weight tiles in flight while this
+// one drains: back-to-back decode GEMMs keep HBM busy across kernel boundaries.
 #include "ptx.cuh"
 #include "qgemm_sm100.h"
 
@@ -29,39 +36,41 @@
 namespace fb {
 
 // ----------------------------------------------------------------------------------------
-// Per-bit-width format constants
+// Per-format / per-footprint constants
 // ----------------------------------------------------------------------------------------
-template <int BITS>
-struct Fmt;
+template <int BITS, bool SMALL>
+struct Cfg;
 template <>
-struct Fmt<4> {
+struct Cfg<4, false> {
     static constexpr int NJ = 4;        // pair fields per 32-bit word == accumulators per tile
-    static constexpr int CPS = 1;       // 128-column TMEM chunks per 64-k stage
+    static constexpr int CPS = 1;       // TMEM chunks per 64-k stage
     static constexpr int K2C = 32;      // k-pairs per chunk (TMEM columns per j)
     static constexpr int ROWS = 128;    // smem rows per stage
     static constexpr int LUTN = 256;    // table2 entries
     static constexpr int SCH = 8;       // scale groups per smem scale chunk
     static constexpr int STAGE_READERS = 4;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int MIN_BLOCKS = 1;
 };
 template <>
-struct Fmt<2> {
-    static constexpr int NJ = 8;
-    static constexpr int CPS = 2;
-    static constexpr int K2C = 16;
-    static constexpr int ROWS = 128;
-    static constexpr int LUTN = 16;
-    static constexpr int SCH = 8;
-    static constexpr int STAGE_READERS = 8;
+struct Cfg<4, true> {
+    static constexpr int NJ = 4, CPS = 2, K2C = 16, ROWS = 128, LUTN = 256, SCH = 8, STAGE_READERS = 8;
+    static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2;
 };
 template <>
-struct Fmt<3> {
-    static constexpr int NJ = 16;
-    static constexpr int CPS = 4;
-    static constexpr int K2C = 8;
-    static constexpr int ROWS = 384;
-    static constexpr int LUTN = 64;
-    static constexpr int SCH = 4;
-    static constexpr int STAGE_READERS = 8;
+struct Cfg<2, false> {
+    static constexpr int NJ = 8, CPS = 2, K2C = 16, ROWS = 128, LUTN = 16, SCH = 8, STAGE_READERS = 8;
+    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1;
+};
+template <>
+struct Cfg<2, true> {
+    static constexpr int NJ = 8, CPS = 4, K2C = 8, ROWS = 128, LUTN = 16, SCH = 8, STAGE_READERS = 8;
+    static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2;
+};
+template <>
+struct Cfg<3, false> {
+    static constexpr int NJ = 16, CPS = 4, K2C = 8, ROWS = 384, LUTN = 64, SCH = 4, STAGE_READERS = 8;
+    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1;
 };
 
 constexpr int kDequantWarps = 8;
@@ -73,7 +82,6 @@ constexpr int kWarps = 12;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxStages = 8;
 constexpr int kMaxChunkSlots = 3;
-constexpr int kTmemCols = 512;
 constexpr int kStageK = 64;
 
 struct SmemCtl {
@@ -114,11 +122,6 @@ __device__ __forceinline__ Range cta_range(const QgemmParams& p, int b, int grid
     return r;
 }
 
-__device__ __forceinline__ int streamk_it0_of(const QgemmParams& p, int c, int grid) {
-    int total = p.n_tiles * p.m_tiles * p.k_iters;
-    int base = total / grid, rem = total - base * grid;
-    return c * base + min(c, rem);
-}
 __device__ __forceinline__ int streamk_cta_of(const QgemmParams& p, int it, int grid) {
     int total = p.n_tiles * p.m_tiles * p.k_iters;
     int base = total / grid, rem = total - base * grid;
@@ -127,21 +130,20 @@ __device__ __forceinline__ int streamk_cta_of(const QgemmParams& p, int it, int 
 }
 
 // column of N that TMEM lane L / field j of this tile maps to (relative to the tile's first column)
-template <int BITS>
+template <int BITS, int NJ>
 __device__ __forceinline__ int n_local(int L, int j, int tile_p) {
-    constexpr int NJ = Fmt<BITS>::NJ;
     if (BITS == 3 || tile_p == 32) return (L >> 5) * (NJ * 32) + j * 32 + (L & 31);
     return (L >> 6) * (NJ * 64) + j * 64 + (L & 63);
 }
 
 // ----------------------------------------------------------------------------------------
-// Dequantise one 128-column TMEM chunk for lane L:  packed words (smem, 128B-swizzled rows)
-// -> table2 pair lookup (32x lane-replicated LUT: bank == lane, conflict free) -> one
-// mul.{f16,bf16}x2 by the group scale -> tcgen05.st.
+// Dequantise one TMEM chunk for lane L:  packed words (smem, 128B-swizzled rows) -> table2 pair
+// lookup (32x lane-replicated LUT: bank == lane, conflict free) -> one mul.{f16,bf16}x2 by the
+// group scale -> tcgen05.st.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lut_ld(uint32_t lut_lane, uint32_t code) {
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(lut_lane + (code << 7)));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -149,7 +151,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-
+// byte J of w, zero extended (one PRMT)
+template <int J>
+__device__ __forceinline__ uint32_t byte_of(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "n"(0x4440 + J));
+    return r;
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
     asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
@@ -158,57 +166,77 @@ __device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
     return old;
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
-template <int BITS, bool BF16>
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[N]) {
+    static_assert(N == 16 || N == 32, "chunk store width");
+    if constexpr (N == 32) tmem_st_32x32b_x32(taddr, r);
+    else tmem_st_32x32b_x16(taddr, r);
+}
+
+template <int BITS, int K2C, bool BF16>
 struct Dequant;
 
-template <bool BF16>
-struct Dequant<4, BF16> {
-    static __device__ __forceinline__ void run(uint32_t wstage, int /*sub*/, int L, uint32_t lut_lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
+// 4-bit: byte j of word k2 -> column j*K2C + k2
+template <int K2C, bool BF16>
+struct Dequant<4, K2C, BF16> {
+    template <int J>
+    static __device__ __forceinline__ void field(const uint32_t (&w)[K2C], uint32_t lut_lane, uint32_t sc, uint32_t taddr) {
+        uint32_t r[K2C];
+#pragma unroll
+        for (int i = 0; i < K2C; ++i) r[i] = mul2<BF16>(lds32(byte_of<J>(w[i]) * 128u + lut_lane), sc);
+        tmem_st_cols<K2C>(taddr + J * K2C, r);
+    }
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane, const uint32_t* sc,
+                                               uint32_t tchunk) {
         const uint32_t row = wstage + L * 128;
         const int x = L & 7;
-        uint32_t w[32];
+        uint32_t w[K2C];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 v = lds128(row + ((c ^ x) << 4));
+        for (int c = 0; c < K2C / 4; ++c) {
+            uint4 v = lds128(row + (((sub * (K2C / 4) + c) ^ x) << 4));
             w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t r[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                uint32_t code = (w[i] >> (8 * j)) & 0xffu;
-                r[i] = mul2<BF16>(lut_ld(lut_lane, code), sc[j]);
-            }
-            tmem_st_32x32b_x32(tchunk + j * 32, r);
-        }
+        field<0>(w, lut_lane, sc[0], tchunk);
+        field<1>(w, lut_lane, sc[1], tchunk);
+        field<2>(w, lut_lane, sc[2], tchunk);
+        field<3>(w, lut_lane, sc[3], tchunk);
     }
 };
 
-template <bool BF16>
-struct Dequant<2, BF16> {
-    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
+// 2-bit: nibble j of word k2 -> column j*K2C + k2; stores cover 32 columns (32/K2C fields)
+template <int K2C, bool BF16>
+struct Dequant<2, K2C, BF16> {
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane, const uint32_t* sc,
+                                               uint32_t tchunk) {
         const uint32_t row = wstage + L * 128;
         const int x = L & 7;
-        uint32_t w[16];
+        uint32_t w[K2C];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint4 v = lds128(row + (((4 * sub + c) ^ x) << 4));
+        for (int c = 0; c < K2C / 4; ++c) {
+            uint4 v = lds128(row + (((sub * (K2C / 4) + c) ^ x) << 4));
             w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
         }
+        constexpr int FPS = 32 / K2C;   // fields per 32-column store
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
+        for (int jj = 0; jj < 8 / FPS; ++jj) {
             uint32_t r[32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * jj + h;
+            for (int h = 0; h < FPS; ++h) {
+                const int j = FPS * jj + h;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    uint32_t code = (w[i] >> (4 * j)) & 0xfu;
-                    r[h * 16 + i] = mul2<BF16>(lut_ld(lut_lane, code), sc[j]);
+                for (int i = 0; i < K2C; ++i) {
+                    const uint32_t code = (w[i] >> (4 * j)) & 0xfu;
+                    r[h * K2C + i] = mul2<BF16>(lds32(code * 128u + lut_lane), sc[j]);
                 }
             }
             tmem_st_32x32b_x32(tchunk + jj * 32, r);
@@ -216,11 +244,12 @@ struct Dequant<2, BF16> {
     }
 };
 
+// 3-bit (K2C = 8): three words per k2 (plane 0 rows [0,128); planes 1/2 rows [128,384): 64 per
+// 32-row block, second plane +32); 6-bit field j -> column j*8 + k2
 template <bool BF16>
-struct Dequant<3, BF16> {
-    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
-        // plane 0 rows [0,128); planes 1/2 rows [128,384): 64 per 32-row block, second plane +32
+struct Dequant<3, 8, BF16> {
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane, const uint32_t* sc,
+                                               uint32_t tchunk) {
         const uint32_t row0 = wstage + L * 128;
         const uint32_t row1 = wstage + (128 + (L >> 5) * 64 + (L & 31)) * 128;
         const uint32_t row2 = row1 + 32 * 128;
@@ -249,7 +278,7 @@ struct Dequant<3, BF16> {
                     } else {
                         code = (w0[i] >> 30) | ((w1[i] >> 30) << 2) | ((w2[i] >> 30) << 4);
                     }
-                    r[h * 8 + i] = mul2<BF16>(lut_ld(lut_lane, code), sc[j]);
+                    r[h * 8 + i] = mul2<BF16>(lds32(code * 128u + lut_lane), sc[j]);
                 }
             }
             tmem_st_32x32b_x32(tchunk + jj * 32, r);
@@ -260,14 +289,15 @@ struct Dequant<3, BF16> {
 // ----------------------------------------------------------------------------------------
 // The kernel
 // ----------------------------------------------------------------------------------------
-template <int BITS, bool BF16>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BITS, bool BF16, bool SMALL>
+__global__ void __launch_bounds__(kThreads, Cfg<BITS, SMALL>::MIN_BLOCKS)
 qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                    const QgemmParams p) {
-    using F = Fmt<BITS>;
+    using F = Cfg<BITS, SMALL>;
     constexpr int NJ = F::NJ;
     constexpr int CPS = F::CPS;
     constexpr int K2C = F::K2C;
+    constexpr int CC = NJ * K2C;          // TMEM columns per chunk
     constexpr int TN = NJ * 128;
     constexpr int SCH = F::SCH;
 
@@ -288,6 +318,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const Range rg = cta_range(p, blockIdx.x, grid);
 
     // ---- one-time setup -------------------------------------------------------------
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 0] = globaltimer_ns();
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_a);
@@ -308,10 +339,9 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         mbar_fence_init();
     }
     if (warp == kMmaWarp) {
-        tmem_alloc(smem_u32(&ctl->tmem_base), kTmemCols);
+        tmem_alloc(smem_u32(&ctl->tmem_base), F::TMEM_COLS);
         tmem_relinquish();
     }
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 0] = globaltimer_ns();
     {   // lane-replicated LUT: entry e of lane l at lut + e*128 + l*4  (weights-only data: no PDL wait).
         // One global load per entry, staged through the (still unused) scale buffer, then replicated.
         uint32_t* stage = reinterpret_cast<uint32_t*>(sc_gen);
@@ -325,9 +355,9 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
     pdl_launch_dependents();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 1] = globaltimer_ns();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 1] = globaltimer_ns();
 
-    const uint32_t acc_col = p.nchunk * 128;   // accumulators sit after the A chunk slots
+    const uint32_t acc_col = p.nchunk * CC;   // accumulators sit after the A chunk slots
 
     if (warp == kProducerWarp) {
         // =============================== TMA producer ===============================
@@ -381,45 +411,56 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer =================================
-        if (lane == 0 && rg.it1 > rg.it0) {
+        // The whole warp runs the loop (so the address arithmetic stays on the uniform datapath);
+        // one elected lane issues the tcgen05 instructions.
+        if (rg.it1 > rg.it0) {
             const uint32_t idesc = make_idesc_f16(BF16, 128, p.mb);
+            const uint32_t d_base = tmem + acc_col;
             int stage = 0;
             uint32_t phase = 0;
-            int cc = 0;       // chunk counter
+            int slot = 0;
+            uint32_t aphase = 0;
             int seg = 0;
+            bool stamped = false;
             for (int it = rg.it0; it < rg.it1;) {
                 const int tile = it / p.k_iters;
                 const int kb = it - tile * p.k_iters;
                 const int ke = min(p.k_iters, kb + (rg.it1 - it));
                 mbar_wait(smem_u32(&ctl->acc_empty), (seg & 1) ^ 1u, p.diag, p.timeout_ns, SITE_MMA_ACCEMPTY, 0, seg);
                 tc_fence_after();
+                uint32_t acc_flag = 0;   // first MMA of every accumulator overwrites
                 for (int k = kb; k < ke; ++k) {
                     mbar_wait(smem_u32(&ctl->full[stage]), phase, p.diag, p.timeout_ns, SITE_MMA_FULL, stage, it);
-                    if (p.trace != nullptr && cc == 0) p.trace[blockIdx.x * 8 + 2] = globaltimer_ns();
+                    if (p.trace != nullptr && !stamped && lane == 0) { p.trace[blockIdx.x * 16 + 2] = globaltimer_ns(); stamped = true; }
                     const uint64_t bdesc = make_smem_desc_sw128(ring + stage * p.stage_bytes + p.w_bytes);
-#pragma unroll 1
-                    for (int sub = 0; sub < CPS; ++sub, ++cc) {
-                        const int slot = cc % p.nchunk;
-                        const uint32_t apar = (cc / p.nchunk) & 1;
-                        mbar_wait(smem_u32(&ctl->a_full[slot]), apar, p.diag, p.timeout_ns, SITE_MMA_AFULL, slot, cc);
+#pragma unroll
+                    for (int sub = 0; sub < CPS; ++sub) {
+                        mbar_wait(smem_u32(&ctl->a_full[slot]), aphase, p.diag, p.timeout_ns, SITE_MMA_AFULL, slot, k);
                         tc_fence_after();
-                        const bool first = (k == kb) && (sub == 0);
+                        const uint32_t a_base = tmem + slot * CC;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) {
+                            for (int j = 0; j < NJ; ++j) {
 #pragma unroll
-                            for (int kk = 0; kk < K2C / 8; ++kk) {
-                                const uint32_t a_addr = tmem + slot * 128 + j * K2C + kk * 8;
-                                const uint64_t b = bdesc + (uint64_t)((sub * K2C * 4 + kk * 32) >> 4);
-                                tc_mma_ts(tmem + acc_col + j * p.mb, a_addr, b, idesc, (first && kk == 0) ? 0u : 1u);
+                                for (int kk = 0; kk < K2C / 8; ++kk) {
+                                    tc_mma_ts(d_base + j * p.mb, a_base + j * K2C + kk * 8,
+                                              bdesc + (uint64_t)((sub * K2C * 4 + kk * 32) >> 4), idesc,
+                                              kk == 0 ? acc_flag : 1u);
+                                }
                             }
+                            tc_commit(smem_u32(&ctl->a_empty[slot]));
                         }
-                        tc_commit(smem_u32(&ctl->a_empty[slot]));
+                        __syncwarp();
+                        acc_flag = 1;
+                        if (++slot == p.nchunk) { slot = 0; aphase ^= 1u; }
                     }
-                    tc_commit(smem_u32(&ctl->empty[stage]));
+                    if (elect_one()) tc_commit(smem_u32(&ctl->empty[stage]));
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(smem_u32(&ctl->acc_full));
-                if (p.trace != nullptr) p.trace[blockIdx.x * 8 + 3] = globaltimer_ns();
+                if (elect_one()) tc_commit(smem_u32(&ctl->acc_full));
+                __syncwarp();
+                if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 16 + 3] = globaltimer_ns();
                 it += ke - kb;
                 ++seg;
             }
@@ -485,7 +526,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         bool synced = false;
         int nloc[NJ];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) nloc[j] = n_local<BITS>(L, j, p.tile_p);
+        for (int j = 0; j < NJ; ++j) nloc[j] = n_local<BITS, NJ>(L, j, p.tile_p);
 
         for (int it = rg.it0; it < rg.it1;) {
             const int tile = it / p.k_iters;
@@ -534,8 +575,8 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     }
                     mbar_wait(smem_u32(&ctl->a_empty[slot]), apar ^ 1u, p.diag, p.timeout_ns, SITE_DQ_AEMPTY, slot, cc);
                     tc_fence_after();
-                    Dequant<BITS, BF16>::run(ring + stage * p.stage_bytes, sub, L, lut_lane, sc,
-                                             tmem + lane_sel + slot * 128);
+                    Dequant<BITS, K2C, BF16>::run(ring + stage * p.stage_bytes, sub, L, lut_lane, sc,
+                                                  tmem + lane_sel + slot * CC);
                     if (sub + 2 >= CPS) {   // this warp's last read of the stage
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[stage]));
@@ -545,10 +586,10 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[slot]));
                     if (p.dbg != nullptr && blockIdx.x == 0 && cc == 0) {
-                        // debug: read the chunk back out of TMEM (128 lanes x 128 columns)
-                        for (int c4 = 0; c4 < 4; ++c4) {
+                        // debug: read the first chunk back out of TMEM (128 lanes x CC columns, row pitch 128)
+                        for (int c4 = 0; c4 < CC / 32; ++c4) {
                             uint32_t r[32];
-                            tmem_ld_32x32b_x32(tmem + lane_sel + slot * 128 + c4 * 32, r);
+                            tmem_ld_32x32b_x32(tmem + lane_sel + slot * CC + c4 * 32, r);
                             tc_wait_ld();
 #pragma unroll
                             for (int i = 0; i < 32; ++i) p.dbg[L * 128 + c4 * 32 + i] = r[i];
@@ -556,8 +597,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     }
                 }
             }
-            // release the last scale chunk of the segment
-            if (sc_held) {
+            if (sc_held) {   // release the last scale chunk of the segment
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[n_sc & 1]));
                 sc_held = false;
@@ -566,7 +606,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             // ------------------------------- epilogue ------------------------------------
             mbar_wait(smem_u32(&ctl->acc_full), seg & 1, p.diag, p.timeout_ns, SITE_DQ_ACCFULL, 0, seg);
             tc_fence_after();
-            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 8 + 4] = globaltimer_ns();
+            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 16 + 4] = globaltimer_ns();
             if (!synced) { pdl_wait_prior_grids(); synced = true; }   // D / workspace may be in use by the prior grid
             const bool full_k = (kb == 0) && (ke == p.k_iters);
             const int m_base = mt * p.mb;
@@ -607,7 +647,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
-            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 8 + 5] = globaltimer_ns();
+            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 16 + 5] = globaltimer_ns();
 
             if (!full_k) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -634,7 +674,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // is_last is reused by the next segment
-                if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 8 + 6] = globaltimer_ns();
+                if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 16 + 6] = globaltimer_ns();
             }
             it += ke - kb;
             ++seg;
@@ -644,10 +684,10 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     // ---- teardown ------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 7] = globaltimer_ns();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 7] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem, kTmemCols);
+        tmem_dealloc(tmem, F::TMEM_COLS);
     }
 }
 
@@ -683,21 +723,13 @@ static int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* bas
     return r == CUDA_SUCCESS ? FB_OK : FB_ERR_TENSORMAP;
 }
 
-template <int BITS>
-static void plan_sizes(int mb, uint32_t* w_bytes, uint32_t* b_bytes, uint32_t* stage_bytes, uint32_t* fixed_bytes) {
-    using F = Fmt<BITS>;
-    *w_bytes = F::ROWS * 128;
-    *b_bytes = mb * 128;
-    *stage_bytes = (*w_bytes + *b_bytes + 1023u) & ~1023u;
-    *fixed_bytes = F::LUTN * 128 + 2 * F::SCH * F::NJ * 128 * 2 + sizeof(SmemCtl) + 1024 /*alignment slack*/;
-}
-
 int qgemm_max_mb(int bits) { return bits == 4 ? 64 : bits == 2 ? 32 : 16; }
 
-template <int BITS, bool BF16>
+template <int BITS, bool BF16, bool SMALL>
 static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
-    using F = Fmt<BITS>;
+    using F = Cfg<BITS, SMALL>;
     constexpr int TN = F::NJ * 128;
+    constexpr int CC = F::NJ * F::K2C;
     QgemmParams p{};
     p.S = static_cast<const uint16_t*>(a.S);
     p.table2 = static_cast<const uint32_t*>(a.table2);
@@ -711,22 +743,25 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.group_size = a.group_size;
     p.G = a.K / a.group_size;
     p.tile_p = a.tile_p;
-    int mb_max = qgemm_max_mb(BITS);
+    int mb_max = SMALL ? 16 : qgemm_max_mb(BITS);
     int mb = ((a.M + 15) / 16) * 16;
     if (mb > mb_max) mb = mb_max;
-    if (a.force_mb > 0) mb = a.force_mb;
+    if (a.force_mb > 0 && a.force_mb <= mb_max) mb = a.force_mb;
     p.mb = mb;
     p.n_tiles = (a.N + TN - 1) / TN;
     p.m_tiles = (a.M + mb - 1) / mb;
     p.k_iters = a.K / kStageK;
-    p.nchunk = (kTmemCols - F::NJ * mb) / 128;
+    p.nchunk = (F::TMEM_COLS - F::NJ * mb) / CC;
     if (p.nchunk > kMaxChunkSlots) p.nchunk = kMaxChunkSlots;
     if (p.nchunk < 2) return FB_ERR_INTERNAL;
     p.plane1_row0 = (BITS == 3) ? a.N / 16 : 0;
 
-    uint32_t fixed;
-    plan_sizes<BITS>(mb, &p.w_bytes, &p.b_bytes, &p.stage_bytes, &fixed);
-    const uint32_t smem_budget = 232448;   // 227 KB
+    p.w_bytes = F::ROWS * 128;
+    p.b_bytes = mb * 128;
+    p.stage_bytes = (p.w_bytes + p.b_bytes + 1023u) & ~1023u;
+    const uint32_t fixed = F::LUTN * 128 + 2 * F::SCH * F::NJ * 128 * 2 + sizeof(SmemCtl) + 1024 /*alignment slack*/;
+    // 227 KB per CTA alone on an SM; (228 KB - 2 x 1 KB reserved) / 2 = 113 KB when two must fit
+    const uint32_t smem_budget = SMALL ? 115712u : 232448u;
     int stages = (int)((smem_budget - fixed) / p.stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
@@ -762,13 +797,14 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
                       (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.K * 2, kStageK, (uint32_t)mb);
     if (rc != FB_OK) return rc;
 
-    auto kern = qgemm_sm100_kernel<BITS, BF16>;
+    auto kern = qgemm_sm100_kernel<BITS, BF16, SMALL>;
     static bool attr_set[64] = {};
     if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
             cudaGetLastError();
             return FB_ERR_LAUNCH;
         }
+        if (SMALL) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set[a.device] = true;
     }
 
@@ -795,13 +831,21 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 }
 
 int qgemm_launch(const QgemmArgs& a, cudaStream_t stream) {
-    switch (a.num_bits * 2 + (a.bf16 ? 1 : 0)) {
-        case 4 * 2 + 0: return launch_t<4, false>(a, stream);
-        case 4 * 2 + 1: return launch_t<4, true>(a, stream);
-        case 2 * 2 + 0: return launch_t<2, false>(a, stream);
-        case 2 * 2 + 1: return launch_t<2, true>(a, stream);
-        case 3 * 2 + 0: return launch_t<3, false>(a, stream);
-        case 3 * 2 + 1: return launch_t<3, true>(a, stream);
+    // SMALL (2 CTAs/SM) footprint for decode-sized batches; a.variant: -1 auto, 0 LARGE, 1 SMALL
+    bool small = (a.M <= 16) && (a.num_bits == 4 || a.num_bits == 2);
+    if (a.variant == 0) small = false;
+    if (a.variant == 1 && (a.num_bits == 4 || a.num_bits == 2) && a.M <= 16) small = true;
+    switch (a.num_bits * 4 + (a.bf16 ? 2 : 0) + (small ? 1 : 0)) {
+        case 4 * 4 + 0: return launch_t<4, false, false>(a, stream);
+        case 4 * 4 + 1: return launch_t<4, false, true>(a, stream);
+        case 4 * 4 + 2: return launch_t<4, true, false>(a, stream);
+        case 4 * 4 + 3: return launch_t<4, true, true>(a, stream);
+        case 2 * 4 + 0: return launch_t<2, false, false>(a, stream);
+        case 2 * 4 + 1: return launch_t<2, false, true>(a, stream);
+        case 2 * 4 + 2: return launch_t<2, true, false>(a, stream);
+        case 2 * 4 + 3: return launch_t<2, true, true>(a, stream);
+        case 3 * 4 + 0: return launch_t<3, false, false>(a, stream);
+        case 3 * 4 + 2: return launch_t<3, true, false>(a, stream);
     }
     return FB_ERR_BITS;
 }

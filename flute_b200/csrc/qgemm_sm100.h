@@ -36,6 +36,7 @@ struct QgemmArgs {
     int force_stages;
     int force_grid;
     int force_streamk;
+    int variant;   // -1 auto, 0 LARGE (1 CTA/SM), 1 SMALL (2 CTAs/SM)
 };
 
 // Kernel parameters (passed by value).

@@ -129,6 +129,10 @@ FLUTE_B200_API int flute_b200_check(int device);
  * complete, epilogue done, fix-up done, exit.  Pass NULL to switch tracing off. */
 FLUTE_B200_API void flute_b200_set_trace_buffer(void* device_ptr);
 
+/* Test hook: kernel footprint for later qgemm launches: -1 automatic (default), 0 LARGE (1 CTA/SM),
+ * 1 SMALL (2 CTAs/SM; applies when M <= 16 and num_bits is 2 or 4). */
+FLUTE_B200_API void flute_b200_set_variant(int variant);
+
 /* Test hook: like flute_b200_qgemm with explicit tiling overrides (0 / -1 = engine's choice) and an
  * optional device buffer receiving the first dequantised TMEM chunk (128 x 128 uint32). */
 FLUTE_B200_API int flute_b200_qgemm_debug(const void* A, const void* Q, void* D, const void* S, const void* table2, void* workspace,

@@ -267,6 +267,8 @@ def main():
     if args.group:
         from flute_b200 import _lib
         _lib.lib.flute_b200_set_timeout_ms(3000)
+        if os.environ.get("FLUTE_B200_VARIANT"):
+            _lib.lib.flute_b200_set_variant(int(os.environ["FLUTE_B200_VARIANT"]))
         ok = GROUPS[args.group]()
         print(f"GROUP {args.group}: {'PASS' if ok else 'FAIL'}", flush=True)
         sys.exit(0 if ok else 1)

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--force-grid", type=int, default=0)
     ap.add_argument("--force-streamk", type=int, default=-1)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--trace", type=int, default=0, help="print a per-CTA timeline of one isolated launch")
     args = ap.parse_args()
 
@@ -45,6 +46,7 @@ def main():
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     ws = utils.get_workspace_streamk(dev)
+    _lib.lib.flute_b200_set_variant(args.variant)
     bits, group = args.bits, args.group
     table = torch.randn(2 ** bits, device=dev).to(dt)
     table2 = utils.make_qmap2_from_qmap(table)
@@ -72,7 +74,7 @@ def main():
                 launch(i)
             torch.cuda.synchronize()
             if args.trace:
-                tr = torch.zeros((256, 8), dtype=torch.int64, device=dev)
+                tr = torch.zeros((256, 16), dtype=torch.int64, device=dev)
                 _lib.lib.flute_b200_set_trace_buffer(tr.data_ptr())
                 launch(1 % ncopies)
                 torch.cuda.synchronize()
