@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflute_b200.so")
+LIB_PATH = os.path.join(_HERE, "libflute_b200_prof.so" if os.environ.get("FLUTE_B200_PROFILE") == "1"
+                        else "libflute_b200.so")   # _prof: per-role cycle counters, tools/microbench.py only
 
 # every symbol include/flute_b200.h declares
 EXPORTS = (

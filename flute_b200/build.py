@@ -38,16 +38,22 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    if profile:
+        return _build(os.path.join(HERE, "libflute_b200_prof.so"), verbose, ["-DFB_PROFILE=1"], "_obj_prof")
     if not force and not _stale():
         return LIB
-    objdir = os.path.join(HERE, "csrc", "_obj")
+    return _build(LIB, verbose, [], "_obj")
+
+
+def _build(lib_path: str, verbose: bool, extra: list, objname: str) -> str:
+    objdir = os.path.join(HERE, "csrc", objname)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -60,13 +66,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
     link = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-            "-Xlinker", "--exclude-libs,ALL", "-o", LIB, *objs]
+            "-Xlinker", "--exclude-libs,ALL", "-o", lib_path, *objs]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile="--profile" in sys.argv)
     print(path)

@@ -34,6 +34,7 @@ struct DeviceState {
 DeviceState g_dev[kMaxDevices];
 long g_timeout_ms = 10000;
 unsigned long long* g_trace = nullptr;
+int g_ablate = 0;
 int g_variant = -1;                       // test hook: kernel footprint override   // test hook: per-CTA globaltimer stamps
 
 struct DeviceGuard {
@@ -132,6 +133,7 @@ int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* 
     a.dbg = static_cast<uint32_t*>(dbg);
     a.trace = g_trace;
     a.variant = g_variant;
+    a.ablate = g_ablate;
     a.timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
     a.force_mb = force_mb; a.force_stages = force_stages; a.force_grid = force_grid; a.force_streamk = force_streamk;
     rc = fb::qgemm_launch(a, static_cast<cudaStream_t>(stream));
@@ -272,7 +274,11 @@ int flute_b200_version(void) { return FLUTE_B200_VERSION; }
 
 void flute_b200_set_timeout_ms(long ms) { g_timeout_ms = ms; }
 
-void flute_b200_set_variant(int variant) { g_variant = variant; }
+void flute_b200_set_variant(int variant) {
+    g_variant = variant & 0xff;
+    if (g_variant == 0xff) g_variant = -1;
+    g_ablate = (variant >> 8) & 0xff;   // undocumented perf-ablation bits, tools/microbench.py only
+}
 
 void flute_b200_set_trace_buffer(void* device_ptr) { g_trace = static_cast<unsigned long long*>(device_ptr); }
 

@@ -35,6 +35,20 @@
 
 namespace fb {
 
+// Optional per-role cycle accounting (profiling build only: python flute_b200/build.py --profile).
+#ifdef FB_PROFILE
+#define PROF_DECL(...) long long __VA_ARGS__
+#define PROF_T0(t) long long t = clock64()
+#define PROF_ADD(acc, t) do { long long _n = clock64(); acc += _n - t; t = _n; } while (0)
+#define PROF_OUT(slot, v) do { if (p.trace != nullptr) p.trace[blockIdx.x * 32 + (slot)] = (unsigned long long)(v); } while (0)
+#else
+#define PROF_DECL(...)
+#define PROF_T0(t)
+#define PROF_ADD(acc, t)
+#define PROF_OUT(slot, v)
+#endif
+constexpr int kTraceStride = 32;
+
 // ----------------------------------------------------------------------------------------
 // Per-format / per-footprint constants
 // ----------------------------------------------------------------------------------------
@@ -51,26 +65,27 @@ struct Cfg<4, false> {
     static constexpr int STAGE_READERS = 4;
     static constexpr int TMEM_COLS = 512;
     static constexpr int MIN_BLOCKS = 1;
+    static constexpr int LUT_STRIDE = 256;   // bytes between LUT entries: 256 lets ONE prmt build (code << 8) | lane*4
 };
 template <>
 struct Cfg<4, true> {
     static constexpr int NJ = 4, CPS = 2, K2C = 16, ROWS = 128, LUTN = 256, SCH = 8, STAGE_READERS = 8;
-    static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2;
+    static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2, LUT_STRIDE = 128;
 };
 template <>
 struct Cfg<2, false> {
     static constexpr int NJ = 8, CPS = 2, K2C = 16, ROWS = 128, LUTN = 16, SCH = 8, STAGE_READERS = 8;
-    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1;
+    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1, LUT_STRIDE = 128;
 };
 template <>
 struct Cfg<2, true> {
     static constexpr int NJ = 8, CPS = 4, K2C = 8, ROWS = 128, LUTN = 16, SCH = 8, STAGE_READERS = 8;
-    static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2;
+    static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2, LUT_STRIDE = 128;
 };
 template <>
 struct Cfg<3, false> {
     static constexpr int NJ = 16, CPS = 4, K2C = 8, ROWS = 384, LUTN = 64, SCH = 4, STAGE_READERS = 8;
-    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1;
+    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1, LUT_STRIDE = 128;
 };
 
 constexpr int kDequantWarps = 8;
@@ -186,18 +201,40 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)
 template <int BITS, int K2C, bool BF16>
 struct Dequant;
 
-// 4-bit: byte j of word k2 -> column j*K2C + k2
-template <int K2C, bool BF16>
-struct Dequant<4, K2C, BF16> {
+// 4-bit: byte j of word k2 -> column j*K2C + k2.  LUT address of code c for lane l:
+//   STRIDE 256:  lut + ((c << 8) | l*4)         one PRMT merges byte J of w with the lane byte
+//   STRIDE 128:  lut + ((c << 7) | l*4)         PRMT + SHF (ALU pipe) and PRMT + IMAD (FMA pipe) alternate,
+//                                               so neither pipe carries the whole address arithmetic
+template <int J>
+__device__ __forceinline__ uint32_t prmt_code_lane(uint32_t w, uint32_t lane_byte) {
+    uint32_t r;   // bytes: [0] = lane_byte.b0, [1] = w.b<J>, [2] = lane_byte.b1 (0), [3] = lane_byte.b2 (0)
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(lane_byte), "n"(0x6504 + (J << 4)));
+    return r;
+}
+template <int K2C, bool BF16, int STRIDE>
+struct Dequant4 {
     template <int J>
-    static __device__ __forceinline__ void field(const uint32_t (&w)[K2C], uint32_t lut_lane, uint32_t sc, uint32_t taddr) {
+    static __device__ __forceinline__ void field(const uint32_t (&w)[K2C], uint32_t lut, uint32_t lane, uint32_t sc,
+                                                 uint32_t taddr) {
         uint32_t r[K2C];
+        if constexpr (STRIDE == 256) {
+            const uint32_t lane4 = lane * 4;
 #pragma unroll
-        for (int i = 0; i < K2C; ++i) r[i] = mul2<BF16>(lds32(byte_of<J>(w[i]) * 128u + lut_lane), sc);
-        tmem_st_cols<K2C>(taddr + J * K2C, r);
+            for (int i = 0; i < K2C; ++i) r[i] = mul2<BF16>(lds32(prmt_code_lane<J>(w[i], lane4) + lut), sc);
+        } else {
+            const uint32_t lane8 = lane * 8, lut_lane = lut + lane * 4;
+#pragma unroll
+            for (int i = 0; i < K2C; ++i) {
+                uint32_t a;
+                if (i & 1) a = (prmt_code_lane<J>(w[i], lane8) >> 1) + lut;
+                else a = byte_of<J>(w[i]) * 128u + lut_lane;
+                r[i] = mul2<BF16>(lds32(a), sc);
+            }
+        }
+        tmem_st_cols(taddr + J * K2C, r);
     }
-    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane, const uint32_t* sc,
-                                               uint32_t tchunk) {
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
         const uint32_t row = wstage + L * 128;
         const int x = L & 7;
         uint32_t w[K2C];
@@ -206,18 +243,29 @@ struct Dequant<4, K2C, BF16> {
             uint4 v = lds128(row + (((sub * (K2C / 4) + c) ^ x) << 4));
             w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
         }
-        field<0>(w, lut_lane, sc[0], tchunk);
-        field<1>(w, lut_lane, sc[1], tchunk);
-        field<2>(w, lut_lane, sc[2], tchunk);
-        field<3>(w, lut_lane, sc[3], tchunk);
+        field<0>(w, lut, lane, sc[0], tchunk);
+        field<1>(w, lut, lane, sc[1], tchunk);
+        field<2>(w, lut, lane, sc[2], tchunk);
+        field<3>(w, lut, lane, sc[3], tchunk);
+    }
+};
+template <int K2C, bool BF16>
+struct Dequant<4, K2C, BF16> {
+    template <int STRIDE>
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
+        Dequant4<K2C, BF16, STRIDE>::run(wstage, sub, L, lut, lane, sc, tchunk);
     }
 };
 
 // 2-bit: nibble j of word k2 -> column j*K2C + k2; stores cover 32 columns (32/K2C fields)
 template <int K2C, bool BF16>
 struct Dequant<2, K2C, BF16> {
-    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane, const uint32_t* sc,
-                                               uint32_t tchunk) {
+    template <int STRIDE>
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
+        static_assert(STRIDE == 128, "2-bit LUT stride");
+        const uint32_t lut_lane = lut + lane * 4;
         const uint32_t row = wstage + L * 128;
         const int x = L & 7;
         uint32_t w[K2C];
@@ -248,8 +296,11 @@ struct Dequant<2, K2C, BF16> {
 // 32-row block, second plane +32); 6-bit field j -> column j*8 + k2
 template <bool BF16>
 struct Dequant<3, 8, BF16> {
-    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut_lane, const uint32_t* sc,
-                                               uint32_t tchunk) {
+    template <int STRIDE>
+    static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
+                                               const uint32_t* sc, uint32_t tchunk) {
+        static_assert(STRIDE == 128, "3-bit LUT stride");
+        const uint32_t lut_lane = lut + lane * 4;
         const uint32_t row0 = wstage + L * 128;
         const uint32_t row1 = wstage + (128 + (L >> 5) * 64 + (L & 31)) * 128;
         const uint32_t row2 = row1 + 32 * 128;
@@ -307,7 +358,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
     const uint32_t ring = smem_base;
     const uint32_t lut = ring + p.stages * p.stage_bytes;
-    const uint32_t sc_smem = lut + F::LUTN * 128;
+    const uint32_t sc_smem = lut + F::LUTN * F::LUT_STRIDE;
     uint16_t* sc_gen = reinterpret_cast<uint16_t*>(smem_gen + (sc_smem - smem_base));
     constexpr uint32_t kScSlotElems = SCH * TN;
     SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem_gen + (sc_smem + 2 * kScSlotElems * 2 - smem_base));
@@ -318,7 +369,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const Range rg = cta_range(p, blockIdx.x, grid);
 
     // ---- one-time setup -------------------------------------------------------------
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 0] = globaltimer_ns();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * kTraceStride + 0] = globaltimer_ns();
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_a);
@@ -342,20 +393,21 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         tmem_alloc(smem_u32(&ctl->tmem_base), F::TMEM_COLS);
         tmem_relinquish();
     }
-    {   // lane-replicated LUT: entry e of lane l at lut + e*128 + l*4  (weights-only data: no PDL wait).
+    {   // lane-replicated LUT: entry e of lane l at lut + e*LUT_STRIDE + l*4  (weights-only data: no PDL wait).
         // One global load per entry, staged through the (still unused) scale buffer, then replicated.
         uint32_t* stage = reinterpret_cast<uint32_t*>(sc_gen);
         for (int i = threadIdx.x; i < F::LUTN; i += kThreads) stage[i] = __ldg(p.table2 + i);
         __syncthreads();
         uint32_t* lut_gen = reinterpret_cast<uint32_t*>(smem_gen + (lut - smem_base));
-        for (int i = threadIdx.x; i < F::LUTN * 32; i += kThreads) lut_gen[i] = stage[i >> 5];
+        for (int i = threadIdx.x; i < F::LUTN * 32; i += kThreads)
+            lut_gen[(i >> 5) * (F::LUT_STRIDE / 4) + (i & 31)] = stage[i >> 5];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ctl->tmem_base;
     pdl_launch_dependents();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 1] = globaltimer_ns();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * kTraceStride + 1] = globaltimer_ns();
 
     const uint32_t acc_col = p.nchunk * CC;   // accumulators sit after the A chunk slots
 
@@ -366,48 +418,62 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             const uint64_t pol_a = policy_evict_last();
             const int n_it = rg.it1 - rg.it0;
             const int npro = min(p.stages, n_it);
-            auto coords = [&](int it, int& nt, int& mt, int& k) {
-                int tile = it / p.k_iters;
-                k = it - tile * p.k_iters;
-                nt = tile / p.m_tiles;
-                mt = tile - nt * p.m_tiles;
+            // (nt, mt, k) of an iteration, advanced incrementally: no divisions on the per-stage path
+            struct Cur { int nt, mt, k; };
+            auto advance = [&](Cur& c) {
+                if (++c.k == p.k_iters) {
+                    c.k = 0;
+                    if (++c.mt == p.m_tiles) { c.mt = 0; ++c.nt; }
+                }
             };
-            auto load_w = [&](int it, int s) {
-                int nt, mt, k;
-                coords(it, nt, mt, k);
+            Cur c0;
+            {
+                const int tile = rg.it0 / p.k_iters;
+                c0.k = rg.it0 - tile * p.k_iters;
+                c0.nt = tile / p.m_tiles;
+                c0.mt = tile - c0.nt * p.m_tiles;
+            }
+            auto load_w = [&](const Cur& c, int s) {
                 const uint32_t dst = ring + s * p.stage_bytes;
                 const uint32_t bar = smem_u32(&ctl->full[s]);
                 if (BITS == 3) {
-                    tma_load_2d(dst, &tmap_w, bar, k * kStageK, nt * 128, pol_w);
-                    tma_load_2d(dst + 128 * 128, &tmap_w, bar, k * kStageK, p.plane1_row0 + nt * 256, pol_w);
-                    tma_load_2d(dst + 256 * 128, &tmap_w, bar, k * kStageK, p.plane1_row0 + nt * 256 + 128, pol_w);
+                    tma_load_2d(dst, &tmap_w, bar, c.k * kStageK, c.nt * 128, pol_w);
+                    tma_load_2d(dst + 128 * 128, &tmap_w, bar, c.k * kStageK, p.plane1_row0 + c.nt * 256, pol_w);
+                    tma_load_2d(dst + 256 * 128, &tmap_w, bar, c.k * kStageK, p.plane1_row0 + c.nt * 256 + 128, pol_w);
                 } else {
-                    tma_load_2d(dst, &tmap_w, bar, k * kStageK, nt * 128, pol_w);
+                    tma_load_2d(dst, &tmap_w, bar, c.k * kStageK, c.nt * 128, pol_w);
                 }
             };
-            auto load_a = [&](int it, int s) {
-                int nt, mt, k;
-                coords(it, nt, mt, k);
-                tma_load_2d(ring + s * p.stage_bytes + p.w_bytes, &tmap_a, smem_u32(&ctl->full[s]), k * kStageK,
-                            mt * p.mb, pol_a);
+            auto load_a = [&](const Cur& c, int s) {
+                tma_load_2d(ring + s * p.stage_bytes + p.w_bytes, &tmap_a, smem_u32(&ctl->full[s]), c.k * kStageK,
+                            c.mt * p.mb, pol_a);
             };
             // Weights never depend on the previous kernel in the stream: start streaming them
             // before the programmatic-dependency wait, activations after it.
+            Cur cw = c0;
             for (int i = 0; i < npro; ++i) {
                 mbar_arrive_expect_tx(smem_u32(&ctl->full[i]), p.w_bytes + p.b_bytes);
-                load_w(rg.it0 + i, i);
+                load_w(cw, i);
+                advance(cw);
             }
             pdl_wait_prior_grids();
-            for (int i = 0; i < npro; ++i) load_a(rg.it0 + i, i);
+            Cur ca = c0;
+            for (int i = 0; i < npro; ++i) { load_a(ca, i); advance(ca); }
             int stage = npro % p.stages;
             uint32_t phase = (npro == p.stages) ? 1u : 0u;
+            PROF_DECL(pw_empty = 0, pw_issue = 0);
+            PROF_T0(pt);
             for (int i = npro; i < n_it; ++i) {
                 mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u, p.diag, p.timeout_ns, SITE_PROD_EMPTY, stage, i);
+                PROF_ADD(pw_empty, pt);
                 mbar_arrive_expect_tx(smem_u32(&ctl->full[stage]), p.w_bytes + p.b_bytes);
-                load_w(rg.it0 + i, stage);
-                load_a(rg.it0 + i, stage);
+                load_w(cw, stage);
+                load_a(cw, stage);
+                advance(cw);
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                PROF_ADD(pw_issue, pt);
             }
+            PROF_OUT(8, pw_empty); PROF_OUT(9, pw_issue); PROF_OUT(10, n_it - npro);
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer =================================
@@ -422,23 +488,29 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             uint32_t aphase = 0;
             int seg = 0;
             bool stamped = false;
+            PROF_DECL(mw_full = 0, mw_afull = 0, mw_issue = 0, mw_acc = 0);
+            PROF_T0(mt_);
             for (int it = rg.it0; it < rg.it1;) {
                 const int tile = it / p.k_iters;
                 const int kb = it - tile * p.k_iters;
                 const int ke = min(p.k_iters, kb + (rg.it1 - it));
                 mbar_wait(smem_u32(&ctl->acc_empty), (seg & 1) ^ 1u, p.diag, p.timeout_ns, SITE_MMA_ACCEMPTY, 0, seg);
                 tc_fence_after();
+                PROF_ADD(mw_acc, mt_);
                 uint32_t acc_flag = 0;   // first MMA of every accumulator overwrites
                 for (int k = kb; k < ke; ++k) {
                     mbar_wait(smem_u32(&ctl->full[stage]), phase, p.diag, p.timeout_ns, SITE_MMA_FULL, stage, it);
-                    if (p.trace != nullptr && !stamped && lane == 0) { p.trace[blockIdx.x * 16 + 2] = globaltimer_ns(); stamped = true; }
+                    PROF_ADD(mw_full, mt_);
+                    if (p.trace != nullptr && !stamped && lane == 0) { p.trace[blockIdx.x * kTraceStride + 2] = globaltimer_ns(); stamped = true; }
                     const uint64_t bdesc = make_smem_desc_sw128(ring + stage * p.stage_bytes + p.w_bytes);
 #pragma unroll
                     for (int sub = 0; sub < CPS; ++sub) {
                         mbar_wait(smem_u32(&ctl->a_full[slot]), aphase, p.diag, p.timeout_ns, SITE_MMA_AFULL, slot, k);
                         tc_fence_after();
+                        PROF_ADD(mw_afull, mt_);
                         const uint32_t a_base = tmem + slot * CC;
                         if (elect_one()) {
+                            if (!(p.ablate & 1))
 #pragma unroll
                             for (int j = 0; j < NJ; ++j) {
 #pragma unroll
@@ -457,13 +529,15 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     if (elect_one()) tc_commit(smem_u32(&ctl->empty[stage]));
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    PROF_ADD(mw_issue, mt_);
                 }
                 if (elect_one()) tc_commit(smem_u32(&ctl->acc_full));
                 __syncwarp();
-                if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 16 + 3] = globaltimer_ns();
+                if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * kTraceStride + 3] = globaltimer_ns();
                 it += ke - kb;
                 ++seg;
             }
+            if (lane == 0) { PROF_OUT(11, mw_full); PROF_OUT(12, mw_afull); PROF_OUT(13, mw_issue); PROF_OUT(14, mw_acc); }
         }
     } else if (warp >= kScaleWarp0) {
         // =============================== scale loaders ==============================
@@ -475,37 +549,56 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             const int kb = it - tile * p.k_iters;
             const int ke = min(p.k_iters, kb + (rg.it1 - it));
             const int nt = tile / p.m_tiles;
-            const int c_first = (kb * kStageK / p.group_size) / SCH;
-            const int c_last = ((ke * kStageK - 1) / p.group_size) / SCH;
+            const int c_first = (kb >> p.group_shift) / SCH;
+            const int c_last = ((ke - 1) >> p.group_shift) / SCH;
             for (int c = c_first; c <= c_last; ++c, ++n_sc) {
                 const int slot = n_sc & 1;
                 const uint32_t par = (n_sc >> 1) & 1;
                 mbar_wait(smem_u32(&ctl->sc_empty[slot]), par ^ 1u, p.diag, p.timeout_ns, SITE_SC_EMPTY, slot, n_sc);
                 uint16_t* dst = sc_gen + slot * kScSlotElems;
-                for (int nl = tid; nl < TN; nl += kScaleWarps * 32) {
-                    const int n = nt * TN + nl;
-                    uint16_t v[SCH];
+                // every row this thread owns is fetched before anything is stored: one memory latency per
+                // chunk instead of one per row
+                constexpr int RPT = TN / (kScaleWarps * 32);   // rows per thread
+                if (vec_ok) {
+                    uint4 q[RPT];
 #pragma unroll
-                    for (int g = 0; g < SCH; ++g) v[g] = 0;
-                    if (n < p.N) {
-                        const uint16_t* src = p.S + (size_t)n * p.G + c * SCH;
-                        if (vec_ok) {
+                    for (int r = 0; r < RPT; ++r) {
+                        const int n = nt * TN + tid + r * (kScaleWarps * 32);
+                        q[r] = make_uint4(0, 0, 0, 0);
+                        if (n < p.N) {
+                            const uint16_t* src = p.S + (size_t)n * p.G + c * SCH;
                             if constexpr (SCH == 8) {
-                                uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
-                                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
-                                v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+                                q[r] = __ldg(reinterpret_cast<const uint4*>(src));
                             } else {
-                                uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
-                                v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+                                const uint2 h = __ldg(reinterpret_cast<const uint2*>(src));
+                                q[r].x = h.x; q[r].y = h.y;
                             }
-                        } else {
-#pragma unroll
-                            for (int g = 0; g < SCH; ++g)
-                                if (c * SCH + g < p.G) v[g] = __ldg(src + g);
                         }
                     }
 #pragma unroll
-                    for (int g = 0; g < SCH; ++g) dst[g * TN + nl] = v[g];
+                    for (int r = 0; r < RPT; ++r) {
+                        const int nl = tid + r * (kScaleWarps * 32);
+                        const uint32_t w4[4] = {q[r].x, q[r].y, q[r].z, q[r].w};
+#pragma unroll
+                        for (int g = 0; g < SCH; ++g) dst[g * TN + nl] = (uint16_t)(w4[g >> 1] >> ((g & 1) * 16));
+                    }
+                } else {
+                    for (int r0 = 0; r0 < RPT; r0 += 4) {
+                        uint16_t v[4][SCH];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int n = nt * TN + tid + (r0 + r) * (kScaleWarps * 32);
+#pragma unroll
+                            for (int g = 0; g < SCH; ++g)
+                                v[r][g] = (n < p.N && c * SCH + g < p.G) ? __ldg(p.S + (size_t)n * p.G + c * SCH + g) : (uint16_t)0;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int nl = tid + (r0 + r) * (kScaleWarps * 32);
+#pragma unroll
+                            for (int g = 0; g < SCH; ++g) dst[g * TN + nl] = v[r][g];
+                        }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_full[slot]));
@@ -518,12 +611,18 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         const int q = warp & 3;                 // TMEM lane quarter
         const int L = q * 32 + lane;            // TMEM lane == packed row within the tile
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t lut_lane = lut + lane * 4;
-        int it_local = 0;                       // stage counter
+        int stage = 0;                          // smem ring position of the current iteration
+        uint32_t sphase = 0;
+        int slot = 0;                           // TMEM chunk slot of the NEXT chunk (all chunks, both groups)
+        uint32_t apar = 0;
+        uint32_t cpar = 0;                      // parity of the running chunk counter
         int n_sc = -1;                          // index of the scale chunk currently held
         bool sc_held = false;
         int seg = 0;
         bool synced = false;
+        bool dbg_done = false;
+        PROF_DECL(dw_sc = 0, dw_full = 0, dw_aempty = 0, dw_run = 0, dw_st = 0, dw_epi = 0, dw_chunks = 0);
+        PROF_T0(dt_);
         int nloc[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) nloc[j] = n_local<BITS, NJ>(L, j, p.tile_p);
@@ -535,11 +634,9 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             const int nt = tile / p.m_tiles;
             const int mt = tile - nt * p.m_tiles;
             int cur_sc = -1;
-            for (int k = kb; k < ke; ++k, ++it_local) {
-                const int stage = it_local % p.stages;
-                const uint32_t sphase = (it_local / p.stages) & 1;
+            for (int k = kb; k < ke; ++k) {
                 // ---- scale chunk bookkeeping (every warp consumes every chunk) ----
-                const int g = (k * kStageK) / p.group_size;
+                const int g = k >> p.group_shift;
                 const int sc_id = g / SCH;
                 if (sc_id != cur_sc) {
                     if (sc_held) {
@@ -552,17 +649,22 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     mbar_wait(smem_u32(&ctl->sc_full[n_sc & 1]), (n_sc >> 1) & 1, p.diag, p.timeout_ns, SITE_DQ_SCALE,
                               n_sc & 1, n_sc);
                 }
+                PROF_ADD(dw_sc, dt_);
                 bool touched = false;
 #pragma unroll 1
                 for (int sub = 0; sub < CPS; ++sub) {
-                    const int cc = it_local * CPS + sub;
-                    if ((cc & 1) != group) continue;
+                    // counters advance for every chunk; only this group's chunks are processed
+                    const int my_slot = slot;
+                    const uint32_t my_apar = apar;
+                    const bool mine = (cpar == (uint32_t)group);
+                    cpar ^= 1u;
+                    if (++slot == p.nchunk) { slot = 0; apar ^= 1u; }
+                    if (!mine) continue;
                     if (!touched) {
-                        mbar_wait(smem_u32(&ctl->full[stage]), sphase, p.diag, p.timeout_ns, SITE_DQ_FULL, stage, it_local);
+                        mbar_wait(smem_u32(&ctl->full[stage]), sphase, p.diag, p.timeout_ns, SITE_DQ_FULL, stage, k);
                         touched = true;
                     }
-                    const int slot = cc % p.nchunk;
-                    const uint32_t apar = (cc / p.nchunk) & 1;
+                    PROF_ADD(dw_full, dt_);
                     // group scales for this lane's NJ columns, replicated into both halves
                     uint32_t sc[NJ];
                     {
@@ -573,29 +675,38 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                             sc[j] = s | (s << 16);
                         }
                     }
-                    mbar_wait(smem_u32(&ctl->a_empty[slot]), apar ^ 1u, p.diag, p.timeout_ns, SITE_DQ_AEMPTY, slot, cc);
+                    mbar_wait(smem_u32(&ctl->a_empty[my_slot]), my_apar ^ 1u, p.diag, p.timeout_ns, SITE_DQ_AEMPTY, my_slot, k);
                     tc_fence_after();
-                    Dequant<BITS, K2C, BF16>::run(ring + stage * p.stage_bytes, sub, L, lut_lane, sc,
-                                                  tmem + lane_sel + slot * CC);
+                    PROF_ADD(dw_aempty, dt_);
+                    if (!(p.ablate & 2))
+                        Dequant<BITS, K2C, BF16>::template run<F::LUT_STRIDE>(ring + stage * p.stage_bytes, sub, L, lut,
+                                                                              (uint32_t)lane, sc, tmem + lane_sel + my_slot * CC);
                     if (sub + 2 >= CPS) {   // this warp's last read of the stage
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[stage]));
                     }
+                    PROF_ADD(dw_run, dt_);
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[slot]));
-                    if (p.dbg != nullptr && blockIdx.x == 0 && cc == 0) {
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[my_slot]));
+                    PROF_ADD(dw_st, dt_);
+#ifdef FB_PROFILE
+                    ++dw_chunks;
+#endif
+                    if (p.dbg != nullptr && blockIdx.x == 0 && !dbg_done) {
+                        dbg_done = true;
                         // debug: read the first chunk back out of TMEM (128 lanes x CC columns, row pitch 128)
                         for (int c4 = 0; c4 < CC / 32; ++c4) {
                             uint32_t r[32];
-                            tmem_ld_32x32b_x32(tmem + lane_sel + slot * CC + c4 * 32, r);
+                            tmem_ld_32x32b_x32(tmem + lane_sel + my_slot * CC + c4 * 32, r);
                             tc_wait_ld();
 #pragma unroll
                             for (int i = 0; i < 32; ++i) p.dbg[L * 128 + c4 * 32 + i] = r[i];
                         }
                     }
                 }
+                if (++stage == p.stages) { stage = 0; sphase ^= 1u; }
             }
             if (sc_held) {   // release the last scale chunk of the segment
                 __syncwarp();
@@ -604,9 +715,10 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             }
 
             // ------------------------------- epilogue ------------------------------------
+            PROF_ADD(dw_sc, dt_);
             mbar_wait(smem_u32(&ctl->acc_full), seg & 1, p.diag, p.timeout_ns, SITE_DQ_ACCFULL, 0, seg);
             tc_fence_after();
-            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 16 + 4] = globaltimer_ns();
+            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * kTraceStride + 4] = globaltimer_ns();
             if (!synced) { pdl_wait_prior_grids(); synced = true; }   // D / workspace may be in use by the prior grid
             const bool full_k = (kb == 0) && (ke == p.k_iters);
             const int m_base = mt * p.mb;
@@ -647,7 +759,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
-            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 16 + 5] = globaltimer_ns();
+            if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * kTraceStride + 5] = globaltimer_ns();
 
             if (!full_k) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -674,17 +786,25 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");   // is_last is reused by the next segment
-                if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * 16 + 6] = globaltimer_ns();
+                if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * kTraceStride + 6] = globaltimer_ns();
             }
+            PROF_ADD(dw_epi, dt_);
             it += ke - kb;
             ++seg;
         }
+#ifdef FB_PROFILE
+        if (lane == 0 && (warp == 0 || warp == 4)) {
+            const int o = (warp == 0) ? 16 : 24;
+            PROF_OUT(o + 0, dw_sc); PROF_OUT(o + 1, dw_full); PROF_OUT(o + 2, dw_aempty); PROF_OUT(o + 3, dw_run);
+            PROF_OUT(o + 4, dw_st); PROF_OUT(o + 5, dw_epi); PROF_OUT(o + 6, dw_chunks);
+        }
+#endif
     }
 
     // ---- teardown ------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 16 + 7] = globaltimer_ns();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * kTraceStride + 7] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, F::TMEM_COLS);
@@ -738,10 +858,12 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.diag = a.diag;
     p.dbg = a.dbg;
     p.trace = a.trace;
+    p.ablate = a.ablate;
     p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.group_size = a.group_size;
     p.G = a.K / a.group_size;
+    p.group_shift = (a.group_size == 64) ? 0 : (a.group_size == 128) ? 1 : 2;   // stages (64 k) per group, log2
     p.tile_p = a.tile_p;
     int mb_max = SMALL ? 16 : qgemm_max_mb(BITS);
     int mb = ((a.M + 15) / 16) * 16;
@@ -759,7 +881,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.w_bytes = F::ROWS * 128;
     p.b_bytes = mb * 128;
     p.stage_bytes = (p.w_bytes + p.b_bytes + 1023u) & ~1023u;
-    const uint32_t fixed = F::LUTN * 128 + 2 * F::SCH * F::NJ * 128 * 2 + sizeof(SmemCtl) + 1024 /*alignment slack*/;
+    const uint32_t fixed = F::LUTN * F::LUT_STRIDE + 2 * F::SCH * F::NJ * 128 * 2 + sizeof(SmemCtl) + 1024 /*alignment slack*/;
     // 227 KB per CTA alone on an SM; (228 KB - 2 x 1 KB reserved) / 2 = 113 KB when two must fit
     const uint32_t smem_budget = SMALL ? 115712u : 232448u;
     int stages = (int)((smem_budget - fixed) / p.stage_bytes);

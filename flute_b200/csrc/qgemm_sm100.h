@@ -36,6 +36,7 @@ struct QgemmArgs {
     int force_stages;
     int force_grid;
     int force_streamk;
+    int ablate;    // perf ablation bits (tests only): 1 skip MMA issue, 2 skip dequant math
     int variant;   // -1 auto, 0 LARGE (1 CTA/SM), 1 SMALL (2 CTAs/SM)
 };
 
@@ -51,11 +52,13 @@ struct QgemmParams {
     uint64_t timeout_ns;
     int M, N, K, G;
     int group_size, tile_p;
+    int group_shift;          // log2(group_size / 64)
     int mb;                   // activation rows per tile == MMA N
     int n_tiles, m_tiles, k_iters;
     int stages, nchunk, streamk;
     uint32_t partial_offset;
     uint32_t stage_bytes, w_bytes, b_bytes;
+    int ablate;
     uint32_t plane1_row0;     // 3-bit: first row of planes 1/2 (N/16)
 };
 

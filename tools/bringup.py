@@ -141,6 +141,8 @@ def group_aux():
 def group_tmem():
     """Single stage, single CTA: check the dequantised TMEM chunk, then the MMA result."""
     from oracle import c_oracle
+    from flute_b200 import _lib
+    _lib.lib.flute_b200_set_variant(0)   # the expected chunk layout below is the LARGE footprint's
     ok = True
     for dtype in ("float16", "bfloat16"):
         bits, group, M, N, K = 4, 64, 1, 512, 64

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--force-streamk", type=int, default=-1)
     ap.add_argument("--json", default=None)
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--ablate", type=int, default=0)
     ap.add_argument("--trace", type=int, default=0, help="print a per-CTA timeline of one isolated launch")
     args = ap.parse_args()
 
@@ -46,7 +47,7 @@ def main():
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     ws = utils.get_workspace_streamk(dev)
-    _lib.lib.flute_b200_set_variant(args.variant)
+    _lib.lib.flute_b200_set_variant((args.variant & 0xff) | (args.ablate << 8))
     bits, group = args.bits, args.group
     table = torch.randn(2 ** bits, device=dev).to(dt)
     table2 = utils.make_qmap2_from_qmap(table)
@@ -74,7 +75,7 @@ def main():
                 launch(i)
             torch.cuda.synchronize()
             if args.trace:
-                tr = torch.zeros((256, 16), dtype=torch.int64, device=dev)
+                tr = torch.zeros((256, 32), dtype=torch.int64, device=dev)
                 _lib.lib.flute_b200_set_trace_buffer(tr.data_ptr())
                 launch(1 % ncopies)
                 torch.cuda.synchronize()
@@ -89,6 +90,16 @@ def main():
                     col = t[:, c]; col = col[col > 0] - t0
                     if col.size:
                         print(f"     {nm:10s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}   (n={col.size})")
+                if os.environ.get("FLUTE_B200_PROFILE") == "1":
+                    prof = [(8, "producer wait-empty"), (9, "producer issue"), (10, "producer iters"), (11, "mma wait-full"),
+                            (12, "mma wait-afull"), (13, "mma issue+commit"), (14, "mma wait-accempty"),
+                            (16, "dq0 scale+loop"), (17, "dq0 wait-full"), (18, "dq0 wait-aempty"), (19, "dq0 run"),
+                            (20, "dq0 wait-st+arrive"), (21, "dq0 epilogue"), (22, "dq0 chunks"),
+                            (24, "dq1 scale+loop"), (25, "dq1 wait-full"), (26, "dq1 wait-aempty"), (27, "dq1 run"),
+                            (28, "dq1 wait-st+arrive"), (29, "dq1 epilogue"), (30, "dq1 chunks")]
+                    for c, nm in prof:
+                        col = t[:, c]
+                        print(f"     {nm:22s} min {col.min():8d} med {int(np.median(col)):8d} max {col.max():8d}")
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
             with torch.cuda.stream(side):
