@@ -40,7 +40,8 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
     if profile:
-        return _build(os.path.join(HERE, "libflute_b200_prof.so"), verbose, ["-DFB_PROFILE=1"], "_obj_prof")
+        extra = ["-DFB_PROFILE=1"] + os.environ.get("FB_EXTRA_DEFINES", "").split()
+        return _build(os.path.join(HERE, "libflute_b200_prof.so"), verbose, extra, "_obj_prof")
     if not force and not _stale():
         return LIB
     return _build(LIB, verbose, [], "_obj")

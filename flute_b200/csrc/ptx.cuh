@@ -256,6 +256,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 // ------------------------------------------------------------------------------------
 // T arithmetic on packed pairs (bit patterns in uint32)
 // ------------------------------------------------------------------------------------
+// round_T(a * b) on packed pairs.  Issued as fma(a, b, -0): bit-identical to the multiply (x*y + (-0) == x*y
+// for every x*y, signed zeros included), but it keeps the work on the FMA pipe -- ptxas otherwise turns half
+// of the bf16 multiplies into HMUL2.BF16_V2, which profiling shows on the (4x slower) XU pipe.
+__device__ __forceinline__ uint32_t neg_zero2() {
+    uint32_t z;
+    asm volatile("mov.b32 %0, 0x80008000;" : "=r"(z));   // volatile: keep it an opaque register operand
+    return z;
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b, uint32_t nz) {
+    uint32_t r;
+    if constexpr (BF16) {
+        asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(nz));
+    } else {
+        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(nz));
+    }
+    return r;
+}
 template <bool BF16>
 __device__ __forceinline__ uint32_t mul2(uint32_t a, uint32_t b) {
     uint32_t r;

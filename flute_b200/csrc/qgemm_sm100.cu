@@ -40,63 +40,75 @@ namespace fb {
 #define PROF_DECL(...) long long __VA_ARGS__
 #define PROF_T0(t) long long t = clock64()
 #define PROF_ADD(acc, t) do { long long _n = clock64(); acc += _n - t; t = _n; } while (0)
-#define PROF_OUT(slot, v) do { if (p.trace != nullptr) p.trace[blockIdx.x * 32 + (slot)] = (unsigned long long)(v); } while (0)
+#define PROF_OUT(slot, v) do { if (p.trace != nullptr) p.trace[blockIdx.x * 48 + (slot)] = (unsigned long long)(v); } while (0)
 #else
 #define PROF_DECL(...)
 #define PROF_T0(t)
 #define PROF_ADD(acc, t)
 #define PROF_OUT(slot, v)
 #endif
-constexpr int kTraceStride = 32;
+constexpr int kTraceStride = 48;
+
+// Pin a kernel parameter in a register for the lifetime of a role's loop.  Without this ptxas re-reads it
+// from the constant bank (LDCU, ~50-100 cycles, serially dependent on the uniform datapath) every iteration;
+// profiling showed ~800 cycles per pipeline stage going to that alone.
+template <typename T>
+__device__ __forceinline__ T pin(T v) {
+    static_assert(sizeof(T) == 4, "pin: 32-bit values");
+    asm volatile("" : "+r"(v));
+    return v;
+}
 
 // ----------------------------------------------------------------------------------------
 // Per-format / per-footprint constants
 // ----------------------------------------------------------------------------------------
 template <int BITS, bool SMALL>
 struct Cfg;
+// NJ    pair fields per 32-bit word == accumulators per tile
+// NG    dequantiser groups (4 warps each, one per TMEM lane quarter); chunk c belongs to group c % NG
+// CPS   TMEM chunks per 64-k stage;  K2C  k-pairs per chunk (TMEM columns per field)
+// ROWS  smem rows per stage;  LUTN  table2 entries;  SCH  scale groups per smem scale chunk
+// LUT_STRIDE  bytes between LUT entries: 256 lets ONE prmt build (code << 8) | lane*4 for 4-bit codes
 template <>
 struct Cfg<4, false> {
-    static constexpr int NJ = 4;        // pair fields per 32-bit word == accumulators per tile
-    static constexpr int CPS = 1;       // TMEM chunks per 64-k stage
-    static constexpr int K2C = 32;      // k-pairs per chunk (TMEM columns per j)
-    static constexpr int ROWS = 128;    // smem rows per stage
-    static constexpr int LUTN = 256;    // table2 entries
-    static constexpr int SCH = 8;       // scale groups per smem scale chunk
-    static constexpr int STAGE_READERS = 4;
-    static constexpr int TMEM_COLS = 512;
-    static constexpr int MIN_BLOCKS = 1;
-    static constexpr int LUT_STRIDE = 256;   // bytes between LUT entries: 256 lets ONE prmt build (code << 8) | lane*4
+    static constexpr int NJ = 4, NG = 4, CPS = 2, K2C = 16, ROWS = 128, LUTN = 256, SCH = 8;
+    static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1, LUT_STRIDE = 256;
 };
 template <>
 struct Cfg<4, true> {
-    static constexpr int NJ = 4, CPS = 2, K2C = 16, ROWS = 128, LUTN = 256, SCH = 8, STAGE_READERS = 8;
+    static constexpr int NJ = 4, NG = 2, CPS = 2, K2C = 16, ROWS = 128, LUTN = 256, SCH = 8;
     static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2, LUT_STRIDE = 128;
 };
 template <>
 struct Cfg<2, false> {
-    static constexpr int NJ = 8, CPS = 2, K2C = 16, ROWS = 128, LUTN = 16, SCH = 8, STAGE_READERS = 8;
+    static constexpr int NJ = 8, NG = 4, CPS = 4, K2C = 8, ROWS = 128, LUTN = 16, SCH = 8;
     static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1, LUT_STRIDE = 128;
 };
 template <>
 struct Cfg<2, true> {
-    static constexpr int NJ = 8, CPS = 4, K2C = 8, ROWS = 128, LUTN = 16, SCH = 8, STAGE_READERS = 8;
+    static constexpr int NJ = 8, NG = 2, CPS = 4, K2C = 8, ROWS = 128, LUTN = 16, SCH = 8;
     static constexpr int TMEM_COLS = 256, MIN_BLOCKS = 2, LUT_STRIDE = 128;
 };
 template <>
 struct Cfg<3, false> {
-    static constexpr int NJ = 16, CPS = 4, K2C = 8, ROWS = 384, LUTN = 64, SCH = 4, STAGE_READERS = 8;
+    static constexpr int NJ = 16, NG = 2, CPS = 4, K2C = 8, ROWS = 384, LUTN = 64, SCH = 4;
     static constexpr int TMEM_COLS = 512, MIN_BLOCKS = 1, LUT_STRIDE = 128;
 };
+template <int BITS, bool SMALL>
+struct Roles {
+    using F = Cfg<BITS, SMALL>;
+    static constexpr int kDequantWarps = F::NG * 4;
+    static constexpr int kProducerWarp = kDequantWarps;
+    static constexpr int kMmaWarp = kDequantWarps + 1;
+    static constexpr int kScaleWarp0 = kDequantWarps + 2;
+    static constexpr int kThreads = (kDequantWarps + 4) * 32;
+    // dequant warps that read one smem stage (each arrives on its `empty` barrier once)
+    static constexpr int kStageReaders = (F::CPS < F::NG ? F::CPS : F::NG) * 4;
+};
 
-constexpr int kDequantWarps = 8;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kScaleWarp0 = 10;
 constexpr int kScaleWarps = 2;
-constexpr int kWarps = 12;
-constexpr int kThreads = kWarps * 32;
 constexpr int kMaxStages = 8;
-constexpr int kMaxChunkSlots = 3;
+constexpr int kMaxChunkSlots = 8;
 constexpr int kStageK = 64;
 
 struct SmemCtl {
@@ -215,12 +227,27 @@ template <int K2C, bool BF16, int STRIDE>
 struct Dequant4 {
     template <int J>
     static __device__ __forceinline__ void field(const uint32_t (&w)[K2C], uint32_t lut, uint32_t lane, uint32_t sc,
-                                                 uint32_t taddr) {
+                                                 uint32_t nz, uint32_t taddr) {
         uint32_t r[K2C];
         if constexpr (STRIDE == 256) {
             const uint32_t lane4 = lane * 4;
+#ifndef FB_ABL
+#define FB_ABL 0
+#endif
+            // compile-time ablations for perf studies (tools only): 4 no TMEM store, 8 no LUT load, 16 no multiply
 #pragma unroll
-            for (int i = 0; i < K2C; ++i) r[i] = mul2<BF16>(lds32(prmt_code_lane<J>(w[i], lane4) + lut), sc);
+            for (int i = 0; i < K2C; ++i) {
+                uint32_t a = prmt_code_lane<J>(w[i], lane4);
+                uint32_t v = (FB_ABL & 8) ? a : lds32(a + lut);
+                r[i] = (FB_ABL & 16) ? (v ^ sc) : mul2<BF16>(v, sc, nz);
+            }
+            if (FB_ABL & 4) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int i = 0; i < K2C; ++i) x ^= r[i];
+                if (x == 0x12345678u) tmem_st_cols(taddr + J * K2C, r);   // keeps r[] live, (almost) never stores
+                return;
+            }
         } else {
             const uint32_t lane8 = lane * 8, lut_lane = lut + lane * 4;
 #pragma unroll
@@ -228,13 +255,13 @@ struct Dequant4 {
                 uint32_t a;
                 if (i & 1) a = (prmt_code_lane<J>(w[i], lane8) >> 1) + lut;
                 else a = byte_of<J>(w[i]) * 128u + lut_lane;
-                r[i] = mul2<BF16>(lds32(a), sc);
+                r[i] = mul2<BF16>(lds32(a), sc, nz);
             }
         }
         tmem_st_cols(taddr + J * K2C, r);
     }
     static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
+                                               const uint32_t* sc, uint32_t nz, uint32_t tchunk) {
         const uint32_t row = wstage + L * 128;
         const int x = L & 7;
         uint32_t w[K2C];
@@ -243,18 +270,18 @@ struct Dequant4 {
             uint4 v = lds128(row + (((sub * (K2C / 4) + c) ^ x) << 4));
             w[4 * c + 0] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
         }
-        field<0>(w, lut, lane, sc[0], tchunk);
-        field<1>(w, lut, lane, sc[1], tchunk);
-        field<2>(w, lut, lane, sc[2], tchunk);
-        field<3>(w, lut, lane, sc[3], tchunk);
+        field<0>(w, lut, lane, sc[0], nz, tchunk);
+        field<1>(w, lut, lane, sc[1], nz, tchunk);
+        field<2>(w, lut, lane, sc[2], nz, tchunk);
+        field<3>(w, lut, lane, sc[3], nz, tchunk);
     }
 };
 template <int K2C, bool BF16>
 struct Dequant<4, K2C, BF16> {
     template <int STRIDE>
     static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
-        Dequant4<K2C, BF16, STRIDE>::run(wstage, sub, L, lut, lane, sc, tchunk);
+                                               const uint32_t* sc, uint32_t nz, uint32_t tchunk) {
+        Dequant4<K2C, BF16, STRIDE>::run(wstage, sub, L, lut, lane, sc, nz, tchunk);
     }
 };
 
@@ -263,7 +290,7 @@ template <int K2C, bool BF16>
 struct Dequant<2, K2C, BF16> {
     template <int STRIDE>
     static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
+                                               const uint32_t* sc, uint32_t nz, uint32_t tchunk) {
         static_assert(STRIDE == 128, "2-bit LUT stride");
         const uint32_t lut_lane = lut + lane * 4;
         const uint32_t row = wstage + L * 128;
@@ -284,7 +311,7 @@ struct Dequant<2, K2C, BF16> {
 #pragma unroll
                 for (int i = 0; i < K2C; ++i) {
                     const uint32_t code = (w[i] >> (4 * j)) & 0xfu;
-                    r[h * K2C + i] = mul2<BF16>(lds32(code * 128u + lut_lane), sc[j]);
+                    r[h * K2C + i] = mul2<BF16>(lds32(code * 128u + lut_lane), sc[j], nz);
                 }
             }
             tmem_st_32x32b_x32(tchunk + jj * 32, r);
@@ -298,7 +325,7 @@ template <bool BF16>
 struct Dequant<3, 8, BF16> {
     template <int STRIDE>
     static __device__ __forceinline__ void run(uint32_t wstage, int sub, int L, uint32_t lut, uint32_t lane,
-                                               const uint32_t* sc, uint32_t tchunk) {
+                                               const uint32_t* sc, uint32_t nz, uint32_t tchunk) {
         static_assert(STRIDE == 128, "3-bit LUT stride");
         const uint32_t lut_lane = lut + lane * 4;
         const uint32_t row0 = wstage + L * 128;
@@ -329,7 +356,7 @@ struct Dequant<3, 8, BF16> {
                     } else {
                         code = (w0[i] >> 30) | ((w1[i] >> 30) << 2) | ((w2[i] >> 30) << 4);
                     }
-                    r[h * 8 + i] = mul2<BF16>(lds32(code * 128u + lut_lane), sc[j]);
+                    r[h * 8 + i] = mul2<BF16>(lds32(code * 128u + lut_lane), sc[j], nz);
                 }
             }
             tmem_st_32x32b_x32(tchunk + jj * 32, r);
@@ -341,14 +368,21 @@ struct Dequant<3, 8, BF16> {
 // The kernel
 // ----------------------------------------------------------------------------------------
 template <int BITS, bool BF16, bool SMALL>
-__global__ void __launch_bounds__(kThreads, Cfg<BITS, SMALL>::MIN_BLOCKS)
+__global__ void __launch_bounds__(Roles<BITS, SMALL>::kThreads, Cfg<BITS, SMALL>::MIN_BLOCKS)
 qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
                    const QgemmParams p) {
     using F = Cfg<BITS, SMALL>;
+    using R = Roles<BITS, SMALL>;
     constexpr int NJ = F::NJ;
+    constexpr int NG = F::NG;
     constexpr int CPS = F::CPS;
     constexpr int K2C = F::K2C;
     constexpr int CC = NJ * K2C;          // TMEM columns per chunk
+    constexpr int kDequantWarps = R::kDequantWarps;
+    constexpr int kProducerWarp = R::kProducerWarp;
+    constexpr int kMmaWarp = R::kMmaWarp;
+    constexpr int kScaleWarp0 = R::kScaleWarp0;
+    constexpr int kThreads = R::kThreads;
     constexpr int TN = NJ * 128;
     constexpr int SCH = F::SCH;
 
@@ -375,7 +409,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         tma_prefetch_desc(&tmap_a);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&ctl->full[s]), 1);
-            mbar_init(smem_u32(&ctl->empty[s]), F::STAGE_READERS + 1);
+            mbar_init(smem_u32(&ctl->empty[s]), R::kStageReaders + 1);
         }
         for (int c = 0; c < kMaxChunkSlots; ++c) {
             mbar_init(smem_u32(&ctl->a_full[c]), 4);
@@ -417,13 +451,16 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             const uint64_t pol_w = policy_evict_first();
             const uint64_t pol_a = policy_evict_last();
             const int n_it = rg.it1 - rg.it0;
-            const int npro = min(p.stages, n_it);
+            const int r_stages = pin(p.stages), r_k_iters = pin(p.k_iters), r_m_tiles = pin(p.m_tiles), r_mb = pin(p.mb);
+            const uint32_t r_stage_bytes = pin(p.stage_bytes), r_w_bytes = pin(p.w_bytes);
+            const uint32_t r_tx_bytes = pin(p.w_bytes + p.b_bytes), r_plane1 = pin(p.plane1_row0);
+            const int npro = min(r_stages, n_it);
             // (nt, mt, k) of an iteration, advanced incrementally: no divisions on the per-stage path
             struct Cur { int nt, mt, k; };
             auto advance = [&](Cur& c) {
-                if (++c.k == p.k_iters) {
+                if (++c.k == r_k_iters) {
                     c.k = 0;
-                    if (++c.mt == p.m_tiles) { c.mt = 0; ++c.nt; }
+                    if (++c.mt == r_m_tiles) { c.mt = 0; ++c.nt; }
                 }
             };
             Cur c0;
@@ -434,43 +471,43 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 c0.mt = tile - c0.nt * p.m_tiles;
             }
             auto load_w = [&](const Cur& c, int s) {
-                const uint32_t dst = ring + s * p.stage_bytes;
+                const uint32_t dst = ring + s * r_stage_bytes;
                 const uint32_t bar = smem_u32(&ctl->full[s]);
                 if (BITS == 3) {
                     tma_load_2d(dst, &tmap_w, bar, c.k * kStageK, c.nt * 128, pol_w);
-                    tma_load_2d(dst + 128 * 128, &tmap_w, bar, c.k * kStageK, p.plane1_row0 + c.nt * 256, pol_w);
-                    tma_load_2d(dst + 256 * 128, &tmap_w, bar, c.k * kStageK, p.plane1_row0 + c.nt * 256 + 128, pol_w);
+                    tma_load_2d(dst + 128 * 128, &tmap_w, bar, c.k * kStageK, r_plane1 + c.nt * 256, pol_w);
+                    tma_load_2d(dst + 256 * 128, &tmap_w, bar, c.k * kStageK, r_plane1 + c.nt * 256 + 128, pol_w);
                 } else {
                     tma_load_2d(dst, &tmap_w, bar, c.k * kStageK, c.nt * 128, pol_w);
                 }
             };
             auto load_a = [&](const Cur& c, int s) {
-                tma_load_2d(ring + s * p.stage_bytes + p.w_bytes, &tmap_a, smem_u32(&ctl->full[s]), c.k * kStageK,
-                            c.mt * p.mb, pol_a);
+                tma_load_2d(ring + s * r_stage_bytes + r_w_bytes, &tmap_a, smem_u32(&ctl->full[s]), c.k * kStageK,
+                            c.mt * r_mb, pol_a);
             };
             // Weights never depend on the previous kernel in the stream: start streaming them
             // before the programmatic-dependency wait, activations after it.
             Cur cw = c0;
             for (int i = 0; i < npro; ++i) {
-                mbar_arrive_expect_tx(smem_u32(&ctl->full[i]), p.w_bytes + p.b_bytes);
+                mbar_arrive_expect_tx(smem_u32(&ctl->full[i]), r_tx_bytes);
                 load_w(cw, i);
                 advance(cw);
             }
             pdl_wait_prior_grids();
             Cur ca = c0;
             for (int i = 0; i < npro; ++i) { load_a(ca, i); advance(ca); }
-            int stage = npro % p.stages;
-            uint32_t phase = (npro == p.stages) ? 1u : 0u;
+            int stage = (npro == r_stages) ? 0 : npro;
+            uint32_t phase = (npro == r_stages) ? 1u : 0u;
             PROF_DECL(pw_empty = 0, pw_issue = 0);
             PROF_T0(pt);
             for (int i = npro; i < n_it; ++i) {
                 mbar_wait(smem_u32(&ctl->empty[stage]), phase ^ 1u, p.diag, p.timeout_ns, SITE_PROD_EMPTY, stage, i);
                 PROF_ADD(pw_empty, pt);
-                mbar_arrive_expect_tx(smem_u32(&ctl->full[stage]), p.w_bytes + p.b_bytes);
+                mbar_arrive_expect_tx(smem_u32(&ctl->full[stage]), r_tx_bytes);
                 load_w(cw, stage);
                 load_a(cw, stage);
                 advance(cw);
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (++stage == r_stages) { stage = 0; phase ^= 1u; }
                 PROF_ADD(pw_issue, pt);
             }
             PROF_OUT(8, pw_empty); PROF_OUT(9, pw_issue); PROF_OUT(10, n_it - npro);
@@ -480,8 +517,10 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         // The whole warp runs the loop (so the address arithmetic stays on the uniform datapath);
         // one elected lane issues the tcgen05 instructions.
         if (rg.it1 > rg.it0) {
-            const uint32_t idesc = make_idesc_f16(BF16, 128, p.mb);
+            const uint32_t idesc = pin(make_idesc_f16(BF16, 128, p.mb));
             const uint32_t d_base = tmem + acc_col;
+            const int r_stages = pin(p.stages), r_nchunk = pin(p.nchunk), r_mb = pin(p.mb);
+            const uint32_t r_stage_bytes = pin(p.stage_bytes), r_w_bytes = pin(p.w_bytes);
             int stage = 0;
             uint32_t phase = 0;
             int slot = 0;
@@ -502,7 +541,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     mbar_wait(smem_u32(&ctl->full[stage]), phase, p.diag, p.timeout_ns, SITE_MMA_FULL, stage, it);
                     PROF_ADD(mw_full, mt_);
                     if (p.trace != nullptr && !stamped && lane == 0) { p.trace[blockIdx.x * kTraceStride + 2] = globaltimer_ns(); stamped = true; }
-                    const uint64_t bdesc = make_smem_desc_sw128(ring + stage * p.stage_bytes + p.w_bytes);
+                    const uint64_t bdesc = make_smem_desc_sw128(ring + stage * r_stage_bytes + r_w_bytes);
 #pragma unroll
                     for (int sub = 0; sub < CPS; ++sub) {
                         mbar_wait(smem_u32(&ctl->a_full[slot]), aphase, p.diag, p.timeout_ns, SITE_MMA_AFULL, slot, k);
@@ -515,7 +554,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                             for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                                 for (int kk = 0; kk < K2C / 8; ++kk) {
-                                    tc_mma_ts(d_base + j * p.mb, a_base + j * K2C + kk * 8,
+                                    tc_mma_ts(d_base + j * r_mb, a_base + j * K2C + kk * 8,
                                               bdesc + (uint64_t)((sub * K2C * 4 + kk * 32) >> 4), idesc,
                                               kk == 0 ? acc_flag : 1u);
                                 }
@@ -524,11 +563,11 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                         }
                         __syncwarp();
                         acc_flag = 1;
-                        if (++slot == p.nchunk) { slot = 0; aphase ^= 1u; }
+                        if (++slot == r_nchunk) { slot = 0; aphase ^= 1u; }
                     }
                     if (elect_one()) tc_commit(smem_u32(&ctl->empty[stage]));
                     __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    if (++stage == r_stages) { stage = 0; phase ^= 1u; }
                     PROF_ADD(mw_issue, mt_);
                 }
                 if (elect_one()) tc_commit(smem_u32(&ctl->acc_full));
@@ -543,18 +582,22 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         // =============================== scale loaders ==============================
         const int tid = (warp - kScaleWarp0) * 32 + lane;
         int n_sc = 0;
+        PROF_DECL(lw_empty = 0, lw_load = 0);
+        PROF_T0(lt_);
         const bool vec_ok = ((p.G % SCH) == 0) && ((reinterpret_cast<uintptr_t>(p.S) & 15) == 0);
+        const int r_gshift = pin(p.group_shift);
         for (int it = rg.it0; it < rg.it1;) {
             const int tile = it / p.k_iters;
             const int kb = it - tile * p.k_iters;
             const int ke = min(p.k_iters, kb + (rg.it1 - it));
             const int nt = tile / p.m_tiles;
-            const int c_first = (kb >> p.group_shift) / SCH;
-            const int c_last = ((ke - 1) >> p.group_shift) / SCH;
+            const int c_first = (kb >> r_gshift) / SCH;
+            const int c_last = ((ke - 1) >> r_gshift) / SCH;
             for (int c = c_first; c <= c_last; ++c, ++n_sc) {
                 const int slot = n_sc & 1;
                 const uint32_t par = (n_sc >> 1) & 1;
                 mbar_wait(smem_u32(&ctl->sc_empty[slot]), par ^ 1u, p.diag, p.timeout_ns, SITE_SC_EMPTY, slot, n_sc);
+                PROF_ADD(lw_empty, lt_);
                 uint16_t* dst = sc_gen + slot * kScSlotElems;
                 // every row this thread owns is fetched before anything is stored: one memory latency per
                 // chunk instead of one per row
@@ -602,30 +645,57 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_full[slot]));
+                PROF_ADD(lw_load, lt_);
             }
             it += ke - kb;
         }
+        if (tid == 0) { PROF_OUT(40, lw_empty); PROF_OUT(41, lw_load); PROF_OUT(42, n_sc); }
     } else {
         // ========================= dequantisers + epilogue ==========================
-        const int group = warp >> 2;            // 0 / 1
+        const int group = warp >> 2;            // 0 .. NG-1
         const int q = warp & 3;                 // TMEM lane quarter
         const int L = q * 32 + lane;            // TMEM lane == packed row within the tile
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        int stage = 0;                          // smem ring position of the current iteration
+        // Per-warp pipeline state.  A group steps directly from one of ITS chunks to the next (chunk ids
+        // group, group + NG, ...): no per-chunk iteration over the other groups' work.
+        int my_il = 0;                          // CTA-local stage index of my next chunk
+        int my_sub = group;                     // sub-chunk (0..CPS-1) of my next chunk inside that stage
+        while (my_sub >= CPS) { my_sub -= CPS; ++my_il; }
+        int stage = my_il;                      // ring slot of stage my_il (my_il < NG <= stages here)
         uint32_t sphase = 0;
-        int slot = 0;                           // TMEM chunk slot of the NEXT chunk (all chunks, both groups)
+        int slot = group;                       // TMEM chunk slot of my next chunk (group < NG <= ... handled below)
         uint32_t apar = 0;
-        uint32_t cpar = 0;                      // parity of the running chunk counter
-        int n_sc = -1;                          // index of the scale chunk currently held
-        bool sc_held = false;
+        int seg_il0 = 0;                        // CTA-local index of the segment's first stage
+        int sc_seg0 = 0;                        // global index of the segment's first scale chunk
+        int sc_cur = -1;                        // global index of the scale chunk currently held (-1: none)
+        int sc_done = 0;                        // scale chunks released so far (every warp releases every chunk once)
         int seg = 0;
         bool synced = false;
         bool dbg_done = false;
-        PROF_DECL(dw_sc = 0, dw_full = 0, dw_aempty = 0, dw_run = 0, dw_st = 0, dw_epi = 0, dw_chunks = 0);
+        const int r_stages = pin(p.stages), r_nchunk = pin(p.nchunk), r_gshift = pin(p.group_shift);
+        const uint32_t r_stage_bytes = pin(p.stage_bytes);
+        while (stage >= r_stages) stage -= r_stages;   // (only if stages < NG)
+        while (slot >= r_nchunk) { slot -= r_nchunk; apar ^= 1u; }
+        const uint32_t r_nz = pin(p.neg_zero2);
+        PROF_DECL(dw_scw = 0, dw_sc = 0, dw_full = 0, dw_aempty = 0, dw_run = 0, dw_st = 0, dw_epi = 0, dw_chunks = 0);
         PROF_T0(dt_);
         int nloc[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) nloc[j] = n_local<BITS, NJ>(L, j, p.tile_p);
+
+        // Release scale chunks [sc_done, upto): the one this warp holds and any it never needed.  A chunk that
+        // was never acquired is first waited for, so no warp can run more than one buffer generation ahead of
+        // the others (each sc_empty phase must collect exactly one arrival per warp).
+        auto release_scales_upto = [&](int upto) {
+            while (sc_done < upto) {
+                if (sc_done != sc_cur)
+                    mbar_wait(smem_u32(&ctl->sc_full[sc_done & 1]), (sc_done >> 1) & 1, p.diag, p.timeout_ns,
+                              SITE_DQ_SCALE, sc_done & 1, sc_done);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[sc_done & 1]));
+                ++sc_done;
+            }
+        };
 
         for (int it = rg.it0; it < rg.it1;) {
             const int tile = it / p.k_iters;
@@ -633,86 +703,80 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             const int ke = min(p.k_iters, kb + (rg.it1 - it));
             const int nt = tile / p.m_tiles;
             const int mt = tile - nt * p.m_tiles;
-            int cur_sc = -1;
-            for (int k = kb; k < ke; ++k) {
-                // ---- scale chunk bookkeeping (every warp consumes every chunk) ----
-                const int g = k >> p.group_shift;
-                const int sc_id = g / SCH;
-                if (sc_id != cur_sc) {
-                    if (sc_held) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[n_sc & 1]));
-                    }
-                    ++n_sc;
-                    sc_held = true;
-                    cur_sc = sc_id;
-                    mbar_wait(smem_u32(&ctl->sc_full[n_sc & 1]), (n_sc >> 1) & 1, p.diag, p.timeout_ns, SITE_DQ_SCALE,
-                              n_sc & 1, n_sc);
+            const int seg_il1 = seg_il0 + (ke - kb);
+            const int scid0 = (kb >> r_gshift) / SCH;                       // first scale chunk id of the segment
+            const int sc_count = ((ke - 1) >> r_gshift) / SCH - scid0 + 1;  // scale chunks the loader makes for it
+            while (my_il < seg_il1) {
+                const int k = kb + (my_il - seg_il0);
+                // ---- scale chunk for this stage ----
+                const int g = k >> r_gshift;
+                const int sc_need = sc_seg0 + (g / SCH - scid0);
+                if (sc_need != sc_cur) {
+                    release_scales_upto(sc_need);       // the one I held and any I skipped over
+                    sc_cur = sc_need;
+                    PROF_ADD(dw_sc, dt_);
+                    mbar_wait(smem_u32(&ctl->sc_full[sc_need & 1]), (sc_need >> 1) & 1, p.diag, p.timeout_ns,
+                              SITE_DQ_SCALE, sc_need & 1, sc_need);
+                    PROF_ADD(dw_scw, dt_);
                 }
                 PROF_ADD(dw_sc, dt_);
-                bool touched = false;
-#pragma unroll 1
-                for (int sub = 0; sub < CPS; ++sub) {
-                    // counters advance for every chunk; only this group's chunks are processed
-                    const int my_slot = slot;
-                    const uint32_t my_apar = apar;
-                    const bool mine = (cpar == (uint32_t)group);
-                    cpar ^= 1u;
-                    if (++slot == p.nchunk) { slot = 0; apar ^= 1u; }
-                    if (!mine) continue;
-                    if (!touched) {
-                        mbar_wait(smem_u32(&ctl->full[stage]), sphase, p.diag, p.timeout_ns, SITE_DQ_FULL, stage, k);
-                        touched = true;
-                    }
-                    PROF_ADD(dw_full, dt_);
-                    // group scales for this lane's NJ columns, replicated into both halves
-                    uint32_t sc[NJ];
-                    {
-                        const uint16_t* src = sc_gen + (n_sc & 1) * kScSlotElems + (g % SCH) * TN;
+                mbar_wait(smem_u32(&ctl->full[stage]), sphase, p.diag, p.timeout_ns, SITE_DQ_FULL, stage, k);
+                PROF_ADD(dw_full, dt_);
+                // group scales for this lane's NJ columns, replicated into both halves
+                uint32_t sc[NJ];
+                {
+                    const uint16_t* src = sc_gen + (sc_need & 1) * kScSlotElems + (g % SCH) * TN;
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) {
-                            uint32_t s = src[nloc[j]];
-                            sc[j] = s | (s << 16);
-                        }
-                    }
-                    mbar_wait(smem_u32(&ctl->a_empty[my_slot]), my_apar ^ 1u, p.diag, p.timeout_ns, SITE_DQ_AEMPTY, my_slot, k);
-                    tc_fence_after();
-                    PROF_ADD(dw_aempty, dt_);
-                    if (!(p.ablate & 2))
-                        Dequant<BITS, K2C, BF16>::template run<F::LUT_STRIDE>(ring + stage * p.stage_bytes, sub, L, lut,
-                                                                              (uint32_t)lane, sc, tmem + lane_sel + my_slot * CC);
-                    if (sub + 2 >= CPS) {   // this warp's last read of the stage
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[stage]));
-                    }
-                    PROF_ADD(dw_run, dt_);
-                    tc_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[my_slot]));
-                    PROF_ADD(dw_st, dt_);
-#ifdef FB_PROFILE
-                    ++dw_chunks;
-#endif
-                    if (p.dbg != nullptr && blockIdx.x == 0 && !dbg_done) {
-                        dbg_done = true;
-                        // debug: read the first chunk back out of TMEM (128 lanes x CC columns, row pitch 128)
-                        for (int c4 = 0; c4 < CC / 32; ++c4) {
-                            uint32_t r[32];
-                            tmem_ld_32x32b_x32(tmem + lane_sel + my_slot * CC + c4 * 32, r);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) p.dbg[L * 128 + c4 * 32 + i] = r[i];
-                        }
+                    for (int j = 0; j < NJ; ++j) {
+                        uint32_t s = src[nloc[j]];
+                        sc[j] = s | (s << 16);
                     }
                 }
-                if (++stage == p.stages) { stage = 0; sphase ^= 1u; }
-            }
-            if (sc_held) {   // release the last scale chunk of the segment
+                mbar_wait(smem_u32(&ctl->a_empty[slot]), apar ^ 1u, p.diag, p.timeout_ns, SITE_DQ_AEMPTY, slot, k);
+                tc_fence_after();
+                PROF_ADD(dw_aempty, dt_);
+                if (!(p.ablate & 2))
+                    Dequant<BITS, K2C, BF16>::template run<F::LUT_STRIDE>(ring + stage * r_stage_bytes, my_sub, L, lut,
+                                                                          (uint32_t)lane, sc, r_nz, tmem + lane_sel + slot * CC);
+                if (my_sub + NG >= CPS) {   // this warp's last read of the stage
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->empty[stage]));
+                }
+                PROF_ADD(dw_run, dt_);
+                tc_wait_st();
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[n_sc & 1]));
-                sc_held = false;
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[slot]));
+                PROF_ADD(dw_st, dt_);
+#ifdef FB_PROFILE
+                ++dw_chunks;
+#endif
+                if (p.dbg != nullptr && blockIdx.x == 0 && !dbg_done && group == 0) {
+                    dbg_done = true;
+                    // debug: read the first chunk back out of TMEM (128 lanes x CC columns, row pitch 128)
+                    for (int c4 = 0; c4 < CC / 32; ++c4) {
+                        uint32_t r[32];
+                        tmem_ld_32x32b_x32(tmem + lane_sel + slot * CC + c4 * 32, r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) p.dbg[L * 128 + c4 * 32 + i] = r[i];
+                    }
+                }
+                // ---- advance to my next chunk: chunk id += NG ----
+                my_sub += NG;
+                while (my_sub >= CPS) {
+                    my_sub -= CPS;
+                    ++my_il;
+                    if (++stage == r_stages) { stage = 0; sphase ^= 1u; }
+                }
+                slot += NG;
+                while (slot >= r_nchunk) { slot -= r_nchunk; apar ^= 1u; }
             }
+            // every warp releases every scale chunk of the segment exactly once
+            release_scales_upto(sc_seg0 + sc_count);
+            sc_cur = -1;
+            sc_seg0 += sc_count;
+            seg_il0 = seg_il1;
 
             // ------------------------------- epilogue ------------------------------------
             PROF_ADD(dw_sc, dt_);
@@ -736,7 +800,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                if ((j & 1) != group) continue;
+                if ((j % NG) != group) continue;
                 const int n = n_base + nloc[j];
                 for (int mc = 0; mc < rows_valid; mc += 16) {
                     uint32_t r[16];
@@ -762,7 +826,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * kTraceStride + 5] = globaltimer_ns();
 
             if (!full_k) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
                 if (threadIdx.x == 0) {
                     // release: publishes this CTA's reductions (cumulative through the barrier above);
                     // acquire: the last arriver sees everyone else's.
@@ -771,11 +835,11 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
                     ctl->is_last = last;
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
                 if (ctl->is_last) {
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        if ((j & 1) != group) continue;
+                        if ((j % NG) != group) continue;
                         const int n = n_base + nloc[j];
                         for (int mi = 0; mi < rows_valid; ++mi) {
                             float* src = accum + (j * p.mb + mi) * 128 + L;
@@ -785,7 +849,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // is_last is reused by the next segment
+                asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");   // is_last is reused by the next segment
                 if (p.trace != nullptr && threadIdx.x == 0 && seg == 0) p.trace[blockIdx.x * kTraceStride + 6] = globaltimer_ns();
             }
             PROF_ADD(dw_epi, dt_);
@@ -796,7 +860,7 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         if (lane == 0 && (warp == 0 || warp == 4)) {
             const int o = (warp == 0) ? 16 : 24;
             PROF_OUT(o + 0, dw_sc); PROF_OUT(o + 1, dw_full); PROF_OUT(o + 2, dw_aempty); PROF_OUT(o + 3, dw_run);
-            PROF_OUT(o + 4, dw_st); PROF_OUT(o + 5, dw_epi); PROF_OUT(o + 6, dw_chunks);
+            PROF_OUT(o + 4, dw_st); PROF_OUT(o + 5, dw_epi); PROF_OUT(o + 6, dw_chunks); PROF_OUT(o + 7, dw_scw);
         }
 #endif
     }
@@ -859,6 +923,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.dbg = a.dbg;
     p.trace = a.trace;
     p.ablate = a.ablate;
+    p.neg_zero2 = 0x80008000u;   // (-0, -0) in fp16 and bf16 alike; see ptx.cuh mul2()
     p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.group_size = a.group_size;
@@ -932,7 +997,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(Roles<BITS, SMALL>::kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[1];
@@ -953,9 +1018,11 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 }
 
 int qgemm_launch(const QgemmArgs& a, cudaStream_t stream) {
-    // SMALL (2 CTAs/SM) footprint for decode-sized batches; a.variant: -1 auto, 0 LARGE, 1 SMALL
-    bool small = (a.M <= 16) && (a.num_bits == 4 || a.num_bits == 2);
-    if (a.variant == 0) small = false;
+    // a.variant: -1 auto, 0 LARGE, 1 SMALL.  Measured on B200 (profiles/r01_*): the dequantiser is bound by
+    // shared-memory LUT wavefronts, not by residency, and LARGE (16 dequant warps, 8-stage ring) beats SMALL
+    // (2 CTAs/SM, 3-stage ring) at every Llama shape, so automatic selection is LARGE.  SMALL stays reachable
+    // for the cross-kernel-overlap experiments (flute_b200_set_variant(1)).
+    bool small = false;
     if (a.variant == 1 && (a.num_bits == 4 || a.num_bits == 2) && a.M <= 16) small = true;
     switch (a.num_bits * 4 + (a.bf16 ? 2 : 0) + (small ? 1 : 0)) {
         case 4 * 4 + 0: return launch_t<4, false, false>(a, stream);

@@ -59,6 +59,7 @@ struct QgemmParams {
     uint32_t partial_offset;
     uint32_t stage_bytes, w_bytes, b_bytes;
     int ablate;
+    uint32_t neg_zero2;       // packed (-0, -0): addend that keeps the scale multiply an FMA-pipe instruction
     uint32_t plane1_row0;     // 3-bit: first row of planes 1/2 (N/16)
 };
 

@@ -19,6 +19,7 @@ SHAPE_SETS = {
     "llama8b": [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336)],
     "llama70b": [(10240, 8192), (8192, 8192), (57344, 8192), (8192, 28672)],
     "small": [(4096, 4096)],
+    "gateup": [(28672, 4096)],
 }
 
 
@@ -75,7 +76,7 @@ def main():
                 launch(i)
             torch.cuda.synchronize()
             if args.trace:
-                tr = torch.zeros((256, 32), dtype=torch.int64, device=dev)
+                tr = torch.zeros((256, 48), dtype=torch.int64, device=dev)
                 _lib.lib.flute_b200_set_trace_buffer(tr.data_ptr())
                 launch(1 % ncopies)
                 torch.cuda.synchronize()
@@ -93,10 +94,11 @@ def main():
                 if os.environ.get("FLUTE_B200_PROFILE") == "1":
                     prof = [(8, "producer wait-empty"), (9, "producer issue"), (10, "producer iters"), (11, "mma wait-full"),
                             (12, "mma wait-afull"), (13, "mma issue+commit"), (14, "mma wait-accempty"),
-                            (16, "dq0 scale+loop"), (17, "dq0 wait-full"), (18, "dq0 wait-aempty"), (19, "dq0 run"),
-                            (20, "dq0 wait-st+arrive"), (21, "dq0 epilogue"), (22, "dq0 chunks"),
-                            (24, "dq1 scale+loop"), (25, "dq1 wait-full"), (26, "dq1 wait-aempty"), (27, "dq1 run"),
-                            (28, "dq1 wait-st+arrive"), (29, "dq1 epilogue"), (30, "dq1 chunks")]
+                            (40, "scale wait-empty"), (41, "scale load+store"), (42, "scale chunks"),
+                            (16, "dq0 loop (no waits)"), (23, "dq0 wait-scale"), (17, "dq0 wait-full"), (18, "dq0 wait-aempty"),
+                            (19, "dq0 run"), (20, "dq0 wait-st+arrive"), (21, "dq0 epilogue"), (22, "dq0 chunks"),
+                            (24, "dq1 loop (no waits)"), (31, "dq1 wait-scale"), (25, "dq1 wait-full"), (26, "dq1 wait-aempty"),
+                            (27, "dq1 run"), (28, "dq1 wait-st+arrive"), (29, "dq1 epilogue"), (30, "dq1 chunks")]
                     for c, nm in prof:
                         col = t[:, c]
                         print(f"     {nm:22s} min {col.min():8d} med {int(np.median(col)):8d} max {col.max():8d}")
