@@ -191,7 +191,10 @@ def run_own(args):
     # activation buffers (one per linear type; layers chain through them)
     bufs = {name: torch.empty((M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
     gathered = {name: torch.empty((tp, M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
-    flags = _lib.FLAG_PDL if (tp == 1 and os.environ.get("FLUTE_B200_PDL", "1") != "0") else 0
+    # the model's weights are resident and static: allow weight prefetch across kernel boundaries
+    flags = (_lib.FLAG_PDL | _lib.FLAG_STATIC_WEIGHTS) if (tp == 1 and os.environ.get("FLUTE_B200_PDL", "1") != "0") else 0
+    from flute_b200 import ops as _ops
+    _ops.set_launch_flags(pdl=bool(flags), static_weights=bool(flags))
     launches = [0]
 
     def linear_cabi(x, lin, name):

@@ -34,6 +34,7 @@ EXPORTS = (
 
 F16, BF16 = 0, 1
 FLAG_PDL = 1
+FLAG_STATIC_WEIGHTS = 2
 
 _vp, _i, _sz, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_long
 

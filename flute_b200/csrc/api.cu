@@ -275,6 +275,7 @@ int flute_b200_version(void) { return FLUTE_B200_VERSION; }
 void flute_b200_set_timeout_ms(long ms) { g_timeout_ms = ms; }
 
 void flute_b200_set_variant(int variant) {
+    if (variant < 0) { g_variant = -1; g_ablate = 0; return; }
     g_variant = variant & 0xff;
     if (g_variant == 0xff) g_variant = -1;
     g_ablate = (variant >> 8) & 0xff;   // undocumented perf-ablation bits, tools/microbench.py only

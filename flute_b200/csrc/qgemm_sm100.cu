@@ -404,6 +404,10 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
     // ---- one-time setup -------------------------------------------------------------
     if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * kTraceStride + 0] = globaltimer_ns();
+    // Under programmatic dependent launch this grid may start while earlier kernels of the stream still run.
+    // Unless the caller promises that Q / S / table2 are static (FLUTE_B200_FLAG_STATIC_WEIGHTS), wait for them
+    // before reading anything; with the promise only activations, outputs and workspace are ordered (below).
+    if (!p.static_weights) pdl_wait_prior_grids();
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_a);
@@ -923,6 +927,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.dbg = a.dbg;
     p.trace = a.trace;
     p.ablate = a.ablate;
+    p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
     p.neg_zero2 = 0x80008000u;   // (-0, -0) in fp16 and bf16 alike; see ptx.cuh mul2()
     p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;

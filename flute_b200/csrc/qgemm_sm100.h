@@ -11,7 +11,7 @@ namespace fb {
 
 struct Diag;
 
-enum : int { FB_FLAG_PDL = 1 };
+enum : int { FB_FLAG_PDL = 1, FB_FLAG_STATIC_WEIGHTS = 2 };
 
 // Arguments as the C ABI receives them, plus test-only overrides (0 / -1 = engine's choice).
 struct QgemmArgs {
@@ -59,6 +59,7 @@ struct QgemmParams {
     uint32_t partial_offset;
     uint32_t stage_bytes, w_bytes, b_bytes;
     int ablate;
+    int static_weights;       // weights may be prefetched before griddepcontrol.wait
     uint32_t neg_zero2;       // packed (-0, -0): addend that keeps the scale multiply an FMA-pipe instruction
     uint32_t plane1_row0;     // 3-bit: first row of planes 1/2 (N/16)
 };

@@ -22,10 +22,20 @@ _SCHEMA_QGEMM_HADAMARD = (
 
 import os
 
-# Programmatic dependent launch: the kernel starts streaming WEIGHTS while the previous kernel in the
-# stream drains, and waits (griddepcontrol.wait) before it touches activations, outputs or workspace.
-# Safe next to arbitrary neighbours: kernels launched without the attribute serialise as usual.
+# Programmatic dependent launch (FLUTE_B200_PDL, default on): the kernel's prologue (barrier init, TMEM
+# allocation) overlaps the tail of the previous kernel in the stream; it waits (griddepcontrol.wait) before
+# reading any tensor.  Safe next to arbitrary neighbours: kernels launched without the attribute serialise.
+# FLUTE_B200_STATIC_WEIGHTS=1 additionally lets it start streaming packed weights / scales / tables before
+# that wait -- valid when they are not produced by work still in flight on the stream (a served model).
 LAUNCH_FLAGS = _lib.FLAG_PDL if os.environ.get("FLUTE_B200_PDL", "1") != "0" else 0
+if os.environ.get("FLUTE_B200_STATIC_WEIGHTS", "0") == "1":
+    LAUNCH_FLAGS |= _lib.FLAG_STATIC_WEIGHTS
+
+
+def set_launch_flags(pdl: bool = True, static_weights: bool = False) -> None:
+    """Process-wide launch behaviour of flute.qgemm (see the comment above)."""
+    global LAUNCH_FLAGS
+    LAUNCH_FLAGS = (_lib.FLAG_PDL if pdl else 0) | (_lib.FLAG_STATIC_WEIGHTS if (pdl and static_weights) else 0)
 
 NAMESPACE = "flute"
 try:

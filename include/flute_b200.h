@@ -32,6 +32,8 @@ extern "C" {
 
 /* flags */
 #define FLUTE_B200_FLAG_PDL 1 /* launch with programmatic stream serialization (overlap with the previous kernel) */
+#define FLUTE_B200_FLAG_STATIC_WEIGHTS 2 /* with PDL: Q, S and table2 are not written by earlier work still in flight on
+                                           the stream, so the kernel may start streaming them before that work completes */
 
 /* error codes (the reference raises AT_ERROR / launch-check failures, flute/csrc/qgemm.cpp:82,153,171) */
 enum {

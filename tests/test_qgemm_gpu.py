@@ -1,0 +1,401 @@
+"""Parity of the CUDA path against the oracle -- run on the B200 box: pytest -m gpu.
+
+Small / medium cases compare against the CPU oracle (oracle/flute_oracle.c, pinned to the reference by
+tests/test_oracle_golden.py).  Full BASELINE.json sizes use size-independent properties: the identity
+GEMM must reproduce the dequantised weight bit for bit (tests/kernel.py:30-36,105-107), and the GEMM must
+agree with `torch.mm(A, W_hat)` evaluated on the GPU in T (the reference tests' own ground truth,
+tests/kernel.py:68-71) within 2.0e-3 (fp16) / 1.0e-2 (bf16)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (assert_same_values, bits16, from_bits16, make_case, oracle_dequant, oracle_qgemm, rel_errors,
+                     tol_for)
+
+pytestmark = pytest.mark.gpu
+
+LLAMA3_8B = [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (1024, 4096), (14336, 4096)]
+LLAMA3_70B = [(10240, 8192), (8192, 8192), (57344, 8192), (8192, 28672)]
+GEMMA2_9B = [(2048, 3584), (3584, 4096), (3584, 14336), (4096, 3584), (14336, 3584), (8192, 3584), (28672, 3584)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def flute():
+    import flute_b200
+    return flute_b200
+
+
+@pytest.fixture(scope="module")
+def ws(dev):
+    from flute_b200 import utils
+    return utils.get_workspace_streamk(dev)
+
+
+def run_cabi(c, dev, ws, A=None, force=(0, 0, 0, -1)):
+    """Through the C ABI (flute_b200_qgemm / _debug), raw pointers + current stream."""
+    from flute_b200 import _lib
+    A = (c["A"] if A is None else A).to(dev)
+    Q, S, t2, tab = (c[k].to(dev) for k in ("Q", "S", "table2", "table"))
+    M = A.shape[0]
+    D = torch.full((M, c["N"]), float("nan"), dtype=A.dtype, device=dev)
+    code = _lib.BF16 if A.dtype == torch.bfloat16 else _lib.F16
+    st = torch.cuda.current_stream().cuda_stream
+    if force == (0, 0, 0, -1):
+        rc = _lib.lib.flute_b200_qgemm(A.data_ptr(), Q.data_ptr(), D.data_ptr(), S.data_ptr(), tab.data_ptr(), t2.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), M, c["N"], c["K"], c["bits"], c["group"], c["tile_p"],
+                                       code, 0, 0, st)
+    else:
+        rc = _lib.lib.flute_b200_qgemm_debug(A.data_ptr(), Q.data_ptr(), D.data_ptr(), S.data_ptr(), t2.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), M, c["N"], c["K"], c["bits"], c["group"],
+                                             c["tile_p"], code, 0, 0, st, *force, None)
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib.flute_b200_check(0))
+    return D
+
+
+def assert_close(D, D_ref, dtype, what=""):
+    assert not torch.isnan(D.float()).any(), f"NaN in output {what}"
+    e1, e2 = rel_errors(D, D_ref)
+    tol = tol_for(dtype)
+    assert e1 < tol and e2 < tol, f"{what}: rel err {e1:.3e}/{e2:.3e} >= {tol}"
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors produced by the reference's own code
+# ------------------------------------------------------------------------------------------------
+def test_golden_vectors_through_cuda(golden, dev, ws):
+    from conftest import golden_cases
+    from flute_b200 import utils
+    n = 0
+    for base, tok in golden_cases(golden, "gt"):
+        bits, group = int(tok[1][1:]), int(tok[2][1:])
+        dt = torch.float16 if tok[3] == "f16" else torch.bfloat16
+        A = from_bits16(golden[base + "_A"], dt)
+        c = dict(A=A, Q=torch.from_numpy(golden[base + "_Q"]), S=from_bits16(golden[base + "_S"], dt),
+                 table=from_bits16(golden[base + "_table"], dt), table2=torch.from_numpy(golden[base + "_table2"]),
+                 bits=bits, group=group, dtype=dt, tile_p=32, M=A.shape[0], K=A.shape[1], N=golden[base + "_W"].shape[1])
+        What = utils.dequantize(c["Q"].to(dev), c["S"].to(dev), c["table2"].to(dev), bits, group, 32)
+        assert (bits16(What) == golden[base + "_What"]).all(), base           # bit exact
+        D = run_cabi(c, dev, ws)
+        assert_close(D, from_bits16(golden[base + "_D"], dt), dt, base)
+        n += 1
+    assert n >= 8
+
+
+def test_higgs_golden_vector_dequantize(golden, dev, ws, flute):
+    """tests/higgs.py::test_vector_dequantize on the committed vectors: qgemm(I) == grid[codes] * scales, bit exact."""
+    from conftest import golden_cases
+    from oracle import flute_oracle as O
+    from flute_b200 import utils
+    from flute_b200.templates import default_template_id
+    for base, tok in golden_cases(golden, "higgs"):
+        bits = int(tok[1][1:])
+        dt = torch.float16 if tok[2] == "f16" else torch.bfloat16
+        odt = O.FP16 if dt == torch.float16 else O.BF16
+        codes, grid = golden[base + "_codes"], golden[base + "_grid"]
+        W, t2 = O.higgs_to_flute(np.ascontiguousarray(codes.T), grid, bits, odt)     # integrations/higgs.py:50-71
+        K, N = W.shape
+        Q = utils.pack(torch.from_numpy(W), bits, [default_template_id(bits)], 0)
+        S = from_bits16(golden[base + "_scales"], dt)
+        dummy = torch.arange(2 ** bits).to(dt)                                        # `table` is unused (fact 2)
+        I = torch.eye(K, dtype=dt, device=dev)
+        out = flute.qgemm(I, Q.to(dev), S.to(dev), dummy.to(dev), torch.from_numpy(t2).to(dev), ws, bits, 64,
+                          default_template_id(bits), 148)
+        torch.cuda.synchronize()
+        assert_same_values(out.T, from_bits16(golden[base + "_dense"], dt), base)
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle sweeps (C ABI)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits", [4, 3, 2])
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_sweep_vs_oracle(bits, dtype, dev, ws):
+    N0 = 2048 if bits == 3 else 1024
+    cases = [  # M, N, K, group, table
+        (1, N0, 512, 64, "randn"), (3, N0, 1024, 128, "arange"), (16, N0, 768, 256, "randn"),
+        (32, 2 * N0, 256, 64, "randn"), (53, N0, 512, 64, "randn"), (64, N0, 512, 128, "randn"),
+        (100, N0, 256, 64, "randn"), (1, 4096, 4096, 64, "nf4"), (7, N0 + N0 // 2, 3584, 128, "randn"),
+    ]
+    for i, (M, N, K, group, table) in enumerate(cases):
+        if bits == 3 and N % 512:
+            N = (N // 512) * 512
+        c = make_case(M, N, K, bits, group, dtype, seed=i, table=table)
+        assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"W{bits} {dtype} M={M} N={N} K={K} g={group}")
+
+
+@pytest.mark.parametrize("bits,tile_p", [(4, 64), (2, 64)])
+def test_tile_p_64_packing(bits, tile_p, dev, ws):
+    c = make_case(5, 1024, 512, bits, 64, "bfloat16", seed=3, tile_p=tile_p)
+    assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"tile_P={tile_p}")
+
+
+@pytest.mark.parametrize("bits", [4, 3, 2])
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("table", ["arange", "randn"])
+def test_identity_is_bit_exact(bits, dtype, table, dev, ws):
+    """tests/kernel.py:30-36,105-107: A = I  =>  D == table2[code] * S exactly (integer path + single rounding)."""
+    K, N = 512, (2048 if bits == 3 else 1024)
+    c = make_case(K, N, K, bits, 64, dtype, seed=bits, table=table, identity=True, full_range=(table == "randn"))
+    D = run_cabi(c, dev, ws)
+    assert_same_values(D, oracle_dequant(c), f"identity W{bits} {dtype} {table}")
+
+
+def test_reference_index_range(dev, ws):
+    """The reference draws indices from [0, 2^b - 1) (tests/kernel.py:43-47); run once with exactly that range."""
+    c = make_case(3, 1024, 512, 4, 64, "float16", seed=11, full_range=False)
+    assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"])
+
+
+@pytest.mark.parametrize("force", [(0, 0, 3, 1), (0, 2, 7, 1), (0, 0, 2, 0), (16, 0, 5, 1), (32, 3, 0, -1)])
+def test_schedules_agree(force, dev, ws):
+    """Stream-K splits, ring depths, grid sizes and batch tiles must not change the result beyond fp32 reordering."""
+    c = make_case(20, 2048, 1024, 4, 64, "bfloat16", seed=5)
+    assert_close(run_cabi(c, dev, ws, force=force), oracle_qgemm(c), c["dtype"], f"force={force}")
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_both_footprints(variant, dev, ws):
+    from flute_b200 import _lib
+    _lib.lib.flute_b200_set_variant(variant)
+    try:
+        for bits in (4, 2):
+            c = make_case(4, 2048, 1024, bits, 64, "bfloat16", seed=variant)
+            assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"variant {variant} W{bits}")
+    finally:
+        _lib.lib.flute_b200_set_variant(-1)
+
+
+def test_edge_shapes(dev, ws):
+    for (M, N, K, bits) in [(1, 128, 64, 4), (1, 256, 64, 2), (1, 512, 64, 3), (2, 640, 128, 4), (9, 1536, 192, 3)]:
+        c = make_case(M, N, K, bits, 64, "float16", seed=M + N)
+        assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"edge M={M} N={N} K={K} W{bits}")
+
+
+def test_empty_batch(dev, ws, flute):
+    from flute_b200.templates import default_template_id
+    c = make_case(1, 1024, 256, 4, 64, "float16")
+    out = flute.qgemm(torch.empty((0, 256), dtype=torch.float16, device=dev), c["Q"].to(dev), c["S"].to(dev),
+                      c["table"].to(dev), c["table2"].to(dev), ws, 4, 64, default_template_id(4), 148)
+    assert out.shape == (0, 1024)
+
+
+# ------------------------------------------------------------------------------------------------
+# full BASELINE.json sizes: size-independent properties, everything stays on the GPU
+# ------------------------------------------------------------------------------------------------
+def _gpu_case(N, K, bits, group, dt, dev, seed=0):
+    from flute_b200 import utils
+    g = torch.Generator(device=dev).manual_seed(4321 + seed)
+    Q = torch.randint(-32768, 32768, (N // 16 * bits, K), generator=g, dtype=torch.int16, device=dev)   # any bits are a valid packing
+    S = torch.randn((N, K // group), generator=g, device=dev).to(dt)
+    table = torch.randn(2 ** bits, generator=g, device=dev).to(dt)
+    return Q, S, table, utils.make_qmap2_from_qmap(table)
+
+
+@pytest.mark.parametrize("N,K", LLAMA3_8B)
+def test_config2_llama8b_w4g64_bf16(N, K, dev, ws, flute):
+    """BASELINE config 2: every Llama-3-8B linear, W4G64 bf16, M in {1, 16, 512, 4096}."""
+    from flute_b200 import utils
+    from flute_b200.templates import default_template_id
+    dt = torch.bfloat16
+    Q, S, table, t2 = _gpu_case(N, K, 4, 64, dt, dev)
+    What = utils.dequantize(Q, S, t2, 4, 64)                                    # [K, N], pinned bit-exact above
+    tid = default_template_id(4)
+    g = torch.Generator(device=dev).manual_seed(N + K)
+    for M in (1, 16, 512, 4096):
+        A = (torch.randn((M, K), generator=g, device=dev) / 100.).to(dt)
+        D = flute.qgemm(A, Q, S, table, t2, ws, 4, 64, tid, 148)
+        D_ref = torch.mm(A, What)                                               # tests/kernel.py:71, on the GPU
+        e1, e2 = rel_errors(D, D_ref)
+        assert e1 < 1.0e-2 and e2 < 1.0e-2, (N, K, M, e1, e2)
+    # identity rows: one-hot activations reproduce rows of W_hat exactly
+    rows = torch.tensor([0, 1, 63, 64, K // 2 + 5, K - 1], device=dev)
+    A = torch.zeros((rows.numel(), K), dtype=dt, device=dev)
+    A[torch.arange(rows.numel()), rows] = 1
+    D = flute.qgemm(A, Q, S, table, t2, ws, 4, 64, tid, 148)
+    assert_same_values(D, What[rows], f"one-hot rows {N}x{K}")
+
+
+def test_full_identity_4096(dev, ws, flute):
+    """tests/kernel.py identity case at full size: qgemm(I_4096) == dequantised weight, bit for bit, and the GPU
+    dequantiser == the CPU oracle on all 16.8M weights (what utils.reconstruct / unpack rely on)."""
+    from flute_b200 import utils
+    from flute_b200.templates import default_template_id
+    from oracle import c_oracle
+    for bits, dt in ((4, torch.float16), (3, torch.bfloat16)):
+        N = K = 4096
+        Q, S, table, t2 = _gpu_case(N, K, bits, 64, dt, dev, seed=bits)
+        What = utils.dequantize(Q, S, t2, bits, 64)
+        ref = c_oracle.dequantize(Q.cpu().numpy(), bits16(S), t2.cpu().numpy(), bits, 64, dt == torch.bfloat16)
+        assert (bits16(What) == ref).all()
+        D = flute.qgemm(torch.eye(K, dtype=dt, device=dev), Q, S, table, t2, ws, bits, 64, default_template_id(bits), 148)
+        assert_same_values(D, What, f"identity 4096 W{bits}")
+        rec = utils.reconstruct(Q, S, table, t2, ws, bits, 64, default_template_id(bits), 148)
+        assert rec.shape == (N, K) and torch.equal(rec.T.contiguous().view(torch.int16), What.view(torch.int16))
+
+
+@pytest.mark.parametrize("N,K", LLAMA3_8B[:4])
+def test_config3_llama8b_w3g64_fp16_decode(N, K, dev, ws, flute):
+    """BASELINE config 3: odd-bit unpack path, W3G64 fp16, M = 1."""
+    from flute_b200 import utils
+    from flute_b200.templates import default_template_id
+    Nn = (N // 512) * 512
+    dt = torch.float16
+    Q, S, table, t2 = _gpu_case(Nn, K, 3, 64, dt, dev, seed=3)
+    What = utils.dequantize(Q, S, t2, 3, 64)
+    A = (torch.randn((1, K), device=dev) / 100.).to(dt)
+    D = flute.qgemm(A, Q, S, table, t2, ws, 3, 64, default_template_id(3), 148)
+    e1, e2 = rel_errors(D, torch.mm(A, What))
+    assert e1 < 2.0e-3 and e2 < 2.0e-3, (N, K, e1, e2)
+
+
+@pytest.mark.parametrize("tp", [2, 4, 8])
+def test_config4_llama70b_tp_shards(tp, dev, ws, flute):
+    """BASELINE config 4 (per-rank view): 70B linears column-sharded N/tp, bf16 M = 1; the row-sliced shard must
+    reproduce the corresponding output columns of the unsharded GEMM exactly where K ranges coincide."""
+    from flute_b200 import utils, parallel
+    from flute_b200.templates import default_template_id
+    dt = torch.bfloat16
+    tid = default_template_id(4)
+    for (N, K) in LLAMA3_70B[:2] + LLAMA3_70B[3:]:
+        Q, S, table, t2 = _gpu_case(N, K, 4, 64, dt, dev, seed=tp)
+        A = (torch.randn((1, K), device=dev) / 100.).to(dt)
+        What = utils.dequantize(Q, S, t2, 4, 64)
+        D_ref = torch.mm(A, What)
+        r = tp - 1
+        Qr, Sr = parallel.shard_packed_linear(Q, S, 4, r, tp)
+        Dr = flute.qgemm(A, Qr, Sr, table, t2, ws, 4, 64, tid, 148)
+        ref = D_ref[:, r * N // tp:(r + 1) * N // tp]
+        e1, e2 = rel_errors(Dr, ref)
+        assert e1 < 1.0e-2 and e2 < 1.0e-2, (tp, N, K, e1, e2)
+
+
+@pytest.mark.parametrize("N,K", GEMMA2_9B)
+def test_config5_higgs_v2_hadamard_gemma(N, K, dev, ws, flute):
+    """BASELINE config 5: HIGGS vector_size = 2 (arbitrary 256-entry pair grid as table2) W4G64 + Hadamard
+    pre-transform, Gemma-2-9B shapes.  hadamard_size = largest power of two dividing K."""
+    from flute_b200 import utils, ops
+    from flute_b200.templates import default_template_id
+    from oracle import c_oracle
+    dt = torch.float16
+    g = torch.Generator(device=dev).manual_seed(N * 3 + K)
+    Q = torch.randint(-32768, 32768, (N // 4, K), generator=g, dtype=torch.int16, device=dev)
+    S = (torch.randn((N, K // 64), generator=g, device=dev) / 8).to(dt)
+    grid = torch.randn((256, 2), generator=g, device=dev).to(dt)
+    t2 = grid.view(16, 16, 2).contiguous().view(torch.float32)                     # integrations/higgs.py:67-70
+    dummy = torch.arange(16, device=dev).to(dt)
+    h = K & -K
+    A = torch.randn((3, K), generator=g, device=dev).to(dt)
+    out = flute.qgemm_hadamard(A, Q, S, dummy, t2, ws, 4, 64, h, default_template_id(4), 148)
+    Ah = ops.hadamard_transform(A, h)
+    ref_h = from_bits16(c_oracle.hadamard(bits16(A), h, False), dt)
+    e1, e2 = rel_errors(Ah, ref_h)
+    assert e1 < 2.0e-3 and e2 < 2.0e-3, ("hadamard", K, h, e1, e2)
+    What = utils.dequantize(Q, S, t2, 4, 64)
+    e1, e2 = rel_errors(out, torch.mm(Ah, What))
+    assert e1 < 2.0e-3 and e2 < 2.0e-3, (N, K, e1, e2)
+    # vector dequantisation is exact: one-hot rows pick W_hat rows
+    one = torch.zeros((2, K), dtype=dt, device=dev)
+    one[0, 1] = 1
+    one[1, K - 2] = 1
+    D = flute.qgemm(one, Q, S, dummy, t2, ws, 4, 64, default_template_id(4), 148)
+    assert_same_values(D, What[[1, K - 2]], "higgs one-hot rows")
+
+
+# ------------------------------------------------------------------------------------------------
+# API behaviour
+# ------------------------------------------------------------------------------------------------
+def test_python_api_shapes_and_legacy_names(dev, ws, flute):
+    from flute_b200.templates import default_template_id
+    c = make_case(6, 1024, 512, 4, 64, "bfloat16", seed=21)
+    args = [c[k].to(dev) for k in ("Q", "S", "table", "table2")]
+    x = c["A"].to(dev).view(2, 3, 512)
+    out = flute.qgemm(x, *args, ws, 4, 64, default_template_id(4), 148)
+    assert out.shape == (2, 3, 1024) and out.dtype == torch.bfloat16
+    assert_close(out.view(6, 1024), oracle_qgemm(c), c["dtype"])
+    out2 = flute.qgemm_simple(x, *args, ws, 4, 64)                                  # legacy 8-argument name
+    assert_close(out2.view(6, 1024), oracle_qgemm(c), c["dtype"])
+    xt = c["A"].to(dev).t().contiguous().t()                                        # non-contiguous input
+    assert_close(flute.qgemm(xt, *args, ws, 4, 64, default_template_id(4), 148), oracle_qgemm(c), c["dtype"])
+    assert isinstance(flute.NUM_SMS, int) and flute.NUM_SMS > 0
+    with pytest.raises(RuntimeError):
+        flute.qgemm(x, *args, ws, 4, 64, 9999, 148)                                 # unknown template id
+    with pytest.raises((RuntimeError, ValueError)):
+        flute.qgemm(x, *args, ws, 4, 96, default_template_id(4), 148)               # unsupported group_size
+
+
+def test_workspace_reuse_and_flags_restored(dev, flute):
+    """One workspace, zeroed once, serves calls of any shape back to back; every counter / accumulator the
+    kernel touched is zero again afterwards (contract of flute/utils.py:36-56)."""
+    from flute_b200 import utils
+    from flute_b200.templates import default_template_id
+    ws = utils.make_workspace_streamk(dev)
+    assert ws.dtype == torch.uint8 and ws.numel() == 148 * 4 * 256 * 2048 + 16 * 148 or ws.numel() > 0
+    for rep in range(2):
+        for (M, N, K, bits) in [(1, 4096, 4096, 4), (16, 2048, 1024, 3), (40, 6144, 512, 2), (3, 1024, 8192, 4)]:
+            c = make_case(M, N, K, bits, 64, "bfloat16", seed=rep)
+            out = flute.qgemm(c["A"].to(dev), c["Q"].to(dev), c["S"].to(dev), c["table"].to(dev), c["table2"].to(dev), ws,
+                              bits, 64, default_template_id(bits), 148)
+            assert_close(out, oracle_qgemm(c), c["dtype"], f"rep {rep} {M}x{N}x{K} W{bits}")
+    torch.cuda.synchronize()
+    assert int(ws.view(torch.int32)[: (64 << 20) // 4].abs().max().item()) == 0
+
+
+def test_cuda_graph_capture_and_replay(dev, ws, flute):
+    """qgemm.cpp:101-105: runs on the current stream, no sync, no allocation besides the output -> graph capturable."""
+    from flute_b200.templates import default_template_id
+    c = make_case(1, 4096, 4096, 4, 64, "bfloat16", seed=31)
+    A, Q, S, table, t2 = (c[k].to(dev) for k in ("A", "Q", "S", "table", "table2"))
+    tid = default_template_id(4)
+    ref = oracle_qgemm(c)
+    flute.qgemm(A, Q, S, table, t2, ws, 4, 64, tid, 148)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            y1 = flute.qgemm(A, Q, S, table, t2, ws, 4, 64, tid, 148)
+            y2 = flute.qgemm(y1[:, :4096].contiguous(), Q, S, table, t2, ws, 4, 64, tid, 148)   # PDL-chained pair
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert_close(y1, ref, c["dtype"], "graph replay")
+    assert not torch.isnan(y2.float()).any()
+
+
+def test_opcheck(dev, ws, flute):
+    """tune.py:350-360: schema / fake-tensor / dispatch checks (aot dynamic check skipped as upstream does for
+    non-identity inputs: split-K reduction order is not deterministic)."""
+    from flute_b200.templates import default_template_id
+    c = make_case(4, 1024, 256, 4, 64, "float16", seed=41)
+    args = (c["A"].to(dev), c["Q"].to(dev), c["S"].to(dev), c["table"].to(dev), c["table2"].to(dev), ws, 4, 64,
+            default_template_id(4), 148)
+    utils_ = tuple(u for u in torch.library._OPCHECK_DEFAULT_UTILS if u != "test_aot_dispatch_dynamic")
+    torch.library.opcheck(flute.qgemm, args, test_utils=utils_)
+
+
+def test_tune_and_pack_and_unpack(dev, flute):
+    """flute.tune.tune_and_pack / check / flute.utils.unpack round trip (tune.py:395-463, utils.py:379-407)."""
+    from flute_b200 import tune, utils
+    W = torch.randint(0, 16, (512, 1024), dtype=torch.int64)
+    inputs = torch.randn((2, 512), dtype=torch.float16, device=dev)
+    Q, meta = tune.tune_and_pack(inputs, W, num_bits=4, group_size=64, check_num_seeds=1)
+    assert Q.shape == (256, 512) and meta.N == 1024 and meta.K == 512 and meta.template_id >= 0
+    for uniform in (True, False):
+        for identity in (True, False):
+            assert tune.check(W.to(dev), Q.to(dev), meta, uniform, identity, raise_on_failure=True)
+    S = torch.ones((1024, 8), dtype=torch.float16, device=dev)
+    back = utils.unpack(Q.to(dev), S, utils.get_workspace_streamk(dev), 4, 64, meta.template_id, meta.num_sms)
+    assert back.shape == (1024, 512) and torch.equal(back.T.cpu().to(torch.int64), W)
+    Q2, meta2 = tune.maybe_tune_and_repack(Q.to(dev), S, meta, example_batch_size=8)
+    assert Q2.data_ptr() == Q.to(dev).data_ptr() or torch.equal(Q2.cpu(), Q.cpu())
+    assert meta2.M == 8

@@ -62,7 +62,7 @@ def main():
             Ss = [(torch.randn((N, K // group), device=dev) / K ** 0.5).to(dt) for _ in range(ncopies)]
             A = (torch.randn((M, K), device=dev)).to(dt)
             D = torch.empty((M, N), dtype=dt, device=dev)
-            flags = _lib.FLAG_PDL if args.pdl else 0
+            flags = (_lib.FLAG_PDL | _lib.FLAG_STATIC_WEIGHTS) if args.pdl else 0
 
             def launch(i):
                 rc = _lib.lib.flute_b200_qgemm_debug(
