@@ -898,8 +898,8 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-static int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
-                        uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer) {
+int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
     PFN_encodeTiled enc = get_encode_fn();
     if (enc == nullptr) return FB_ERR_DRIVER;
     cuuint64_t dims[2] = {inner, outer};
@@ -907,7 +907,21 @@ static int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* bas
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? FB_OK : FB_ERR_TENSORMAP;
+}
+
+int make_tmap_3d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                 CUtensorMapSwizzle swizzle) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return FB_ERR_DRIVER;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? FB_OK : FB_ERR_TENSORMAP;
 }
 
@@ -983,10 +997,11 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
     CUtensorMap tm_w, tm_a;
     const uint64_t P = (uint64_t)a.N / 16 * BITS;
-    int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, kStageK, 128);
+    int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, kStageK, 128,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
     rc = make_tmap_2d(&tm_a, BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.A,
-                      (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.K * 2, kStageK, (uint32_t)mb);
+                      (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.K * 2, kStageK, (uint32_t)mb, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
 
     auto kern = qgemm_sm100_kernel<BITS, BF16, SMALL>;
@@ -1027,6 +1042,10 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream) {
     // shared-memory LUT wavefronts, not by residency, and LARGE (16 dequant warps, 8-stage ring) beats SMALL
     // (2 CTAs/SM, 3-stage ring) at every Llama shape, so automatic selection is LARGE.  SMALL stays reachable
     // for the cross-kernel-overlap experiments (flute_b200_set_variant(1)).
+    // M <= 16, 2/4-bit: the decode kernel (qgemm_decode_sm100.cu) unless a test pins the general kernel
+    // (variant 0 / 1, or explicit tiling overrides that only the general kernel understands).
+    if (a.variant < 0 && a.force_mb == 0 && a.force_streamk < 0 && qgemm_decode_supported(a))
+        return qgemm_decode_launch(a, stream);
     bool small = false;
     if (a.variant == 1 && (a.num_bits == 4 || a.num_bits == 2) && a.M <= 16) small = true;
     switch (a.num_bits * 4 + (a.bf16 ? 2 : 0) + (small ? 1 : 0)) {

@@ -1,6 +1,7 @@
 // Internal host <-> kernel interface of the sm_100a LUT-qGEMM (not part of the C ABI).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -65,6 +66,15 @@ struct QgemmParams {
 };
 
 int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);
+// decode-shaped kernel (M <= 16, 2/4-bit): qgemm_decode_sm100.cu
+bool qgemm_decode_supported(const QgemmArgs& a);
+int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream);
 int qgemm_max_mb(int bits);
+int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
+
+int make_tmap_3d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                 CUtensorMapSwizzle swizzle);
 
 }  // namespace fb

@@ -91,7 +91,17 @@ def main():
                     col = t[:, c]; col = col[col > 0] - t0
                     if col.size:
                         print(f"     {nm:10s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}   (n={col.size})")
-                if os.environ.get("FLUTE_B200_PROFILE") == "1":
+                if os.environ.get("FLUTE_B200_PROFILE") == "1" and M <= 16 and bits in (2, 4) and args.variant < 0:
+                    prof = [(8, "producer scale blocks"), (9, "producer wait-empty"), (10, "producer W issue"),
+                            (12, "producer iters"), (13, "mma wait-full"), (14, "mma wait-afull"), (15, "mma wait-pempty"),
+                            (16, "mma issue+commit"),
+                            (24, "dq0 wait-full"), (25, "dq0 wait-aempty"), (26, "dq0 pieces"), (27, "dq0 wait-st+arrive"),
+                            (32, "dq5 wait-full"), (33, "dq5 wait-aempty"), (34, "dq5 pieces"), (35, "dq5 wait-st+arrive"),
+                            (40, "apply scale block"), (41, "apply wait-pfull"), (42, "apply ld+fma"), (43, "apply epilogue")]
+                    for c, nm in prof:
+                        col = t[:, c]
+                        print(f"     {nm:26s} min {col.min():8d} med {int(np.median(col)):8d} max {col.max():8d}")
+                elif os.environ.get("FLUTE_B200_PROFILE") == "1":
                     prof = [(8, "producer wait-empty"), (9, "producer issue"), (10, "producer iters"), (11, "mma wait-full"),
                             (12, "mma wait-afull"), (13, "mma issue+commit"), (14, "mma wait-accempty"),
                             (40, "scale wait-empty"), (41, "scale load+store"), (42, "scale chunks"),

@@ -44,10 +44,12 @@ struct Params {
     int loads_per_cta; // contiguous range of loads per CTA
     int total_loads;
     int batch;         // issue this many loads back to back (waits for all their slots first)
+    int extra_a;       // also load a {128B x 16 rows} activation box per load (only 1 row in bounds)
+    int extra_s;       // also load two {16B x 256 rows} scale boxes every 8 loads
     const uint8_t* base;
 };
 
-__global__ void __launch_bounds__(64) probe(const __grid_constant__ CUtensorMap tm, Params p) {
+__global__ void __launch_bounds__(64) probe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tma, const __grid_constant__ CUtensorMap tms, Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t full[16], empty[16];
     const uint32_t ring = (smem_u32(smem) + 1023u) & ~1023u;
@@ -70,7 +72,12 @@ __global__ void __launch_bounds__(64) probe(const __grid_constant__ CUtensorMap 
                 const int ll = l + b;
                 const uint32_t dst = ring + stage * p.load_bytes;
                 const uint32_t bar = smem_u32(&full[stage]);
-                mbar_expect(bar, p.load_bytes);
+                mbar_expect(bar, p.load_bytes + (p.extra_a ? 2048 : 0) + ((p.extra_s && (ll & 7) == 0) ? 8192 : 0));
+                if (p.extra_a) tma2d(ring + p.stages * p.load_bytes, &tma, bar, (ll % kchunks) * 64, 0);
+                if (p.extra_s && (ll & 7) == 0) {
+                    tma2d(ring + p.stages * p.load_bytes + 2048, &tms, bar, ((ll / 8) % 8) * 8, (ll / kchunks) * 512);
+                    tma2d(ring + p.stages * p.load_bytes + 2048 + 4096, &tms, bar, ((ll / 8) % 8) * 8, (ll / kchunks) * 512 + 256);
+                }
                 if (p.mode == 2) {
                     bulk1d(dst, p.base + (size_t)ll * p.load_bytes, p.load_bytes, bar);
                 } else {
@@ -108,8 +115,28 @@ int main(int argc, char** argv) {
     int nsm = 0; CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
-    struct Case { const char* name; int mode, rows, chunks, stages, batch, ctas_per_sm; };
+    struct Case { const char* name; int mode, rows, chunks, stages, batch, ctas_per_sm, extra_a, extra_s; };
+    // activation-like [16, K] and scale-like [P*4, 64] side matrices
+    uint8_t *da, *ds;
+    CK(cudaMalloc(&da, 16 * K * 2)); CK(cudaMemset(da, 1, 16 * K * 2));
+    CK(cudaMalloc(&ds, (size_t)P * 4 * 64 * 2)); CK(cudaMemset(ds, 1, (size_t)P * 4 * 64 * 2));
+    CUtensorMap tma_, tms_;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, 1}; cuuint64_t str[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, 16}; cuuint32_t es[2] = {1, 1};
+        if (enc(&tma_, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, da, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) printf("enc a fail\n");
+        cuuint64_t dims2[2] = {64, (cuuint64_t)P * 4}; cuuint64_t str2[1] = {128};
+        cuuint32_t box2[2] = {8, 256};
+        if (enc(&tms_, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, ds, dims2, str2, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) printf("enc s fail\n");
+    }
     std::vector<Case> cases = {
+        {"2D {128B x 128 rows}  16KB x8 + A box  ", 0, 128, 1, 8, 1, 1, 1, 0},
+        {"2D {128B x 128 rows}  16KB x8 + A + S  ", 0, 128, 1, 8, 1, 1, 1, 1},
+        {"2D {128B x 128 rows}  16KB x8 + S      ", 0, 128, 1, 8, 1, 1, 0, 1},
+        {"2D {128B x 32 rows}    4KB x32         ", 0, 32, 1, 32, 1, 1, 0, 0},
+        {"2D {128B x 64 rows}    8KB x8          ", 0, 64, 1, 8, 1, 1, 0, 0},
         {"2D {128B x 128 rows}  16KB x8 (current)", 0, 128, 1, 8, 1, 1},
         {"2D {128B x 128 rows}  16KB x8 batch4   ", 0, 128, 1, 8, 4, 1},
         {"2D {128B x 128 rows}  16KB x12         ", 0, 128, 1, 12, 1, 1},
@@ -130,7 +157,7 @@ int main(int argc, char** argv) {
     for (auto& c : cases) {
         CUtensorMap tm;
         Params p{};
-        p.mode = c.mode; p.rows = c.rows; p.chunks = c.chunks; p.stages = c.stages; p.K = K; p.P = (int)P; p.batch = c.batch;
+        p.mode = c.mode; p.rows = c.rows; p.chunks = c.chunks; p.stages = c.stages; p.K = K; p.P = (int)P; p.batch = c.batch; p.extra_a = c.extra_a; p.extra_s = c.extra_s;
         p.base = d;
         if (c.mode == 0) {
             cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)P}; cuuint64_t str[1] = {(cuuint64_t)K * 2};
@@ -155,14 +182,14 @@ int main(int argc, char** argv) {
         }
         const int grid = nsm * c.ctas_per_sm;
         p.loads_per_cta = (p.total_loads + grid - 1) / grid;
-        const size_t smem = (size_t)c.stages * p.load_bytes + 1024;
+        const size_t smem = (size_t)c.stages * p.load_bytes + 1024 + 2048 + 8192;
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int w = 0; w < 2; ++w) probe<<<grid, 64, smem>>>(tm, p);
+        for (int w = 0; w < 2; ++w) probe<<<grid, 64, smem>>>(tm, tma_, tms_, p);
         CK(cudaDeviceSynchronize());
         float best = 1e9;
         for (int r = 0; r < 5; ++r) {
             cudaEventRecord(e0);
-            probe<<<grid, 64, smem>>>(tm, p);
+            probe<<<grid, 64, smem>>>(tm, tma_, tms_, p);
             cudaEventRecord(e1);
             CK(cudaEventSynchronize(e1));
             float ms; cudaEventElapsedTime(&ms, e0, e1);
