@@ -291,8 +291,8 @@ int flute_b200_check(int device) {
                                   "dequant:acc_full", "mma:full", "mma:a_full", "mma:acc_empty", "scale:empty", "final"};
     int site = d->site;
     const char* name = (site >= 0 && site <= 10) ? sites[site] : "?";
-    int rc = fail(FB_ERR_KERNEL, "kernel barrier timeout: block %d warp %d waiting at %s[%d] parity %d iter %d", d->block,
-                  d->warp, name, d->index, d->parity, d->iter);
+    int rc = fail(FB_ERR_KERNEL, "kernel barrier timeout: block %d warp %d waiting at %s(site %d)[%d] parity %d iter %d", d->block,
+                  d->warp, name, site, d->index, d->parity, d->iter);
     d->code = 0;
     return rc;
 }

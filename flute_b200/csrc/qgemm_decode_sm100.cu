@@ -113,14 +113,14 @@ struct DecodeParams {
 
 enum : int { DSITE_FULL = 21, DSITE_AEMPTY, DSITE_PFULL, DSITE_SCFULL, DSITE_EMPTY, DSITE_SCEMPTY, DSITE_AFULL, DSITE_PEMPTY };
 
-static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t bar, uint32_t parity, int iter) {
     if (diag != nullptr) {
         diag->block = blockIdx.x;
         diag->warp = threadIdx.x >> 5;
         diag->site = site;
         diag->index = (int)bar;
         diag->parity = (int)parity;
-        diag->iter = 0;
+        diag->iter = iter;
         diag->code = 1;
         __threadfence_system();
     }
@@ -129,7 +129,7 @@ static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t 
 
 // Lean bounded wait: one try_wait on the fast path; the bound is a spin count (each failed try_wait
 // already suspends the warp for a hardware-defined interval), checked out of line.
-__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const DecodeParams& p, int site) {
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const DecodeParams& p, int site, int iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const Decode
         if ((++spins & 0x3ff) == 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) wait_timeout(p.diag, site, bar, parity);   // 4 s: trap, don't hang
+            else if (now - t0 > 4000000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // 4 s: trap, don't hang
         }
     }
 }
@@ -331,7 +331,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
         for (int s = 0; s < AS; ++s) {
-            mbar_init(smem_u32(&ctl->a_full[s]), kDqWarps);
+            mbar_init(smem_u32(&ctl->a_full[s]), (BITS == 4) ? kDqWarps / 2 : kDqWarps);
             mbar_init(smem_u32(&ctl->a_empty[s]), 1);
         }
         for (int s = 0; s < PS; ++s) {
@@ -473,9 +473,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
                         }
                         DPROF_ADD(mw_issue, mt);
                     } else {
+                        // Not mine, but stay in step with every a_full phase: a parity wait is only meaningful for
+                        // the NEXT completion of a barrier, so this warp must not run a whole phase ahead of it.
 #pragma unroll
-                        for (int c = 0; c < CPS; ++c)
+                        for (int c = 0; c < CPS; ++c) {
+                            wait(smem_u32(&ctl->a_full[aslot]), aphase, p, DSITE_AFULL);
                             if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                        }
                     }
                     const bool flush = (((k + 1) & spg_mask) == 0) || (k == ke - 1);
                     if (flush) { grp_first = true; ++f; }
@@ -714,40 +718,57 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
         const uint32_t wrow = (uint32_t)L * 128;
         const int xq = L & 7;
         const bool do_dq = !(p.ablate & 2);
-        int stage = 0;
-        uint32_t fphase = 0;
-        int aslot = 0;
-        uint32_t aphase = 1;               // parity to wait on a_empty (first pass: free)
-        int tstage = 0;                    // ring slot / phase of stage i - AS/CPS (whose completion frees this A slot)
-        uint32_t tphase = 0;
+        // DQG stage groups: with DQG == 2 the 16 warps split into two sets of 8 that convert alternate stages
+        // (each warp: 4 quads = 16 k-pairs of its row).  During the conversion of a stage the shared-memory
+        // crossbar is the limiter (16 B of packed words + 32 x 4 B of LUT reads per lane = 640 wavefronts per
+        // stage); with every warp on the SAME stage the barrier waits of all warps coincide and the crossbar
+        // idles ~1/3 of the time.  Two sets, one stage apart, fill each other's gaps.
+        constexpr int DQG = (BITS == 4) ? 2 : 1;
+        const int grp = (DQG == 2) ? (sw >> 1) : 0;
+        const int hw = (DQG == 2) ? (sw & 1) : sw;          // position inside the set
         DPROF_DECL(dw_full = 0, dw_aempty = 0, dw_piece = 0, dw_st = 0);
         DPROF_T0(dt);
         const int n_it = rg.it1 - rg.it0;
-        for (int i = 0; i < n_it; ++i) {
+        const int S = p.stages;
+        // ring slot / parity of stage i, and of stage t = i - AS/CPS whose completion frees this stage's last A slot
+        int stage = grp % S;
+        uint32_t fphase = (uint32_t)(grp / S) & 1u;
+        int tstage = 0;
+        uint32_t tphase = 0;
+        {
+            const int t0 = grp - AS / CPS + ((grp < AS / CPS) ? DQG * ((AS / CPS - grp + DQG - 1) / DQG) : 0);   // first t >= 0
+            tstage = t0 % S;
+            tphase = (uint32_t)(t0 / S) & 1u;
+        }
+        int chunk = grp * CPS;             // global chunk index of (stage i, c = 0)
+        int aslot = chunk % AS;
+        uint32_t aphase = ((uint32_t)(chunk / AS) & 1u) ^ 1u;
+        for (int i = grp; i < n_it; i += DQG) {
             wait(smem_u32(&ctl->full[stage]), fphase, p, DSITE_FULL);
             DPROF_ADD(dw_full, dt);
             const uint32_t row = ring + stage * kStageBytes + wrow;
 #pragma unroll
             for (int c = 0; c < CPS; ++c) {
-                // the A slot is free once the MMAs that read it have completed: chunk c of stage i - AS/CPS
                 if (c == CPS - 1) {
                     if (i >= AS / CPS) {
                         wait(smem_u32(&ctl->empty[tstage]), tphase, p, DSITE_AEMPTY);
-                        if (++tstage == p.stages) { tstage = 0; tphase ^= 1u; }
+                        tstage += DQG;
+                        if (tstage >= S) { tstage -= S; tphase ^= 1u; }
                     }
                 } else {
-                    wait(smem_u32(&ctl->a_empty[aslot]), aphase, p, DSITE_AEMPTY);
+                    wait(smem_u32(&ctl->a_empty[aslot]), aphase, p, DSITE_AEMPTY, i * 1000 + n_it);
                 }
                 DPROF_ADD(dw_aempty, dt);
                 tc_fence_after();
                 const uint32_t tcol = tmem + lane_sel + aslot * 128;
                 if (do_dq) {
                     if constexpr (BITS == 4) {
-                        // this warp's 8 k-pairs of the stage: 16-byte quads 2*sw and 2*sw + 1 of row L
-                        Piece<4>::run(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, tcol + sw * 8);
+                        // this warp's 16 k-pairs of the stage: 16-byte quads 4*hw .. 4*hw + 3 of row L
+                        Piece<4>::run(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
+                        Piece<4>::run(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
                     } else {
                         // half stage c: quad c*4 + sw
-                        Piece<2>::run(row, (c * 4 + sw) ^ xq, lut, lane4, tcol + sw * 4);
+                        Piece<2>::run(row, (c * 4 + hw) ^ xq, lut, lane4, tcol + hw * 4);
                     }
                 }
                 DPROF_ADD(dw_piece, dt);
@@ -758,7 +779,12 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
                 if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
                 DPROF_ADD(dw_st, dt);
             }
-            if (++stage == p.stages) { stage = 0; fphase ^= 1u; }
+            // skip the chunks of the stages the other set converts
+#pragma unroll
+            for (int x = 0; x < (DQG - 1) * CPS; ++x)
+                if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+            stage += DQG;
+            if (stage >= S) { stage -= S; fphase ^= 1u; }
         }
 #ifdef FB_PROFILE
         if (lane == 0 && (warp == 0 || warp == 5)) {
