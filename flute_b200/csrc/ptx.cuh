@@ -45,7 +45,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory");
     return t;
 }
 

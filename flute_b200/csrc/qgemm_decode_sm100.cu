@@ -70,7 +70,9 @@ constexpr int kMmaWarpB = 19;          // second MMA issuer: flush groups altern
 constexpr int kApplyWarp0 = 20;       // scale/accumulate/epilogue warps, lane quarter = warp & 3
 // apply warps: 4 (each all NJ fields) for M <= 4; 8 (two field halves) when a field needs 16 accumulators
 __host__ __device__ constexpr int apply_warps(int mc) { return mc > 4 ? 8 : 4; }
-__host__ __device__ constexpr int threads_for(int mc) { return (kApplyWarp0 + apply_warps(mc)) * 32; }
+// M <= 4: one more warp copies the scale blocks; M > 4 (8 apply warps, register budget): the activation warp does
+__host__ __device__ constexpr bool has_scale_warp(int mc) { return mc <= 4; }
+__host__ __device__ constexpr int threads_for(int mc) { return (kApplyWarp0 + apply_warps(mc) + (has_scale_warp(mc) ? 1 : 0)) * 32; }
 constexpr int kMaxStages = 10;
 constexpr int kScSlots = 3;
 constexpr int kLutStride = 256;      // bytes between LUT entries: (code << 8) | lane*4 is ONE prmt
@@ -105,7 +107,7 @@ struct DecodeParams {
     int gshift;          // log2(group_size / 64): stages per group
     int n_tiles, k_iters;
     int stages;
-    int tma_scales;      // scale blocks by TMA (G % 8 == 0 and S 16-byte aligned) or by the producer warp
+    int tma_scales;      // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
     int static_weights;
     int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
     uint32_t partial_offset;
@@ -292,8 +294,7 @@ __device__ __forceinline__ float scale_to_f32(uint32_t s16) {
 
 template <int BITS, bool BF16, int MC>
 __global__ void __launch_bounds__(threads_for(MC), 1)
-qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_s, const DecodeParams p) {
+qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodeParams p) {
     using F = DCfg<BITS>;
     constexpr int NJ = F::NJ, CK2 = F::CK2, CPS = F::CPS;
     constexpr int AS = F::A_SLOTS, PS = F::P_SLOTS;
@@ -302,6 +303,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
     constexpr uint32_t kPCol0 = AS * 128;          // P slots sit after the A slots
     constexpr uint32_t kPCols = NJ * kMb;
     constexpr int kApplyWarps = apply_warps(MC);
+    constexpr int kScaleWarp = kApplyWarp0 + kApplyWarps;   // exists iff has_scale_warp(MC)
     constexpr int NFA = NJ / (kApplyWarps / 4);   // fields per apply warp
     static_assert(kPCol0 + PS * kPCols <= 512, "TMEM budget");
 
@@ -325,7 +327,6 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
 
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmap_w);
-        tma_prefetch_desc(&tmap_s);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&ctl->full[s]), 2);   // TMA (expect_tx) + the activation rows
             mbar_init(smem_u32(&ctl->empty[s]), 1);
@@ -339,7 +340,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
             mbar_init(smem_u32(&ctl->p_empty[s]), kApplyWarps);
         }
         for (int s = 0; s < kScSlots; ++s) {
-            mbar_init(smem_u32(&ctl->sc_full[s]), 1);
+            mbar_init(smem_u32(&ctl->sc_full[s]), 32);   // one (deferred) arrival per lane of the activation/scale warp
             mbar_init(smem_u32(&ctl->sc_empty[s]), kApplyWarps);
         }
         mbar_fence_init();
@@ -356,9 +357,46 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
     const uint32_t tmem = ctl->tmem_base;
     pdl_launch_dependents();
 
+    // One step of the scale-block schedule (called once per stage, in stage order, by ONE warp): when stage (tile, k)
+    // starts a new block of 8 groups, copy [tile columns] x [8 groups] (16 bytes per row) into the next scale slot.
+    // cp.async, not TMA: as a TMA box the 512 sixteen-byte rows cost the producer ~2000 cycles of issue time per
+    // block (measured), during which no weight tile could be requested.
+    auto scale_step = [&](int tile, int k, int& nb, int& last_blk) {
+        const int blk = (k >> p.gshift) >> 3;
+        if (blk == last_blk) return;
+        const int slot = nb % kScSlots;
+        const uint32_t par = ((nb / kScSlots) & 1) ^ 1u;
+        wait(smem_u32(&ctl->sc_empty[slot]), par, p, DSITE_SCEMPTY);
+        const uint32_t dst = sc_smem + slot * kScBytes;
+        if (p.tma_scales) {
+#pragma unroll 4
+            for (int r = lane; r < TN; r += 32) {
+                const int n = tile * TN + r;
+                if (n < p.N) {
+                    const uint16_t* src = p.S + (size_t)n * p.G + blk * 8;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 16), "l"(src) : "memory");
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->sc_full[slot])) : "memory");
+        } else {
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(smem_gen + (dst - smem_base));
+            for (int r = lane; r < TN; r += 32) {
+                const int n = tile * TN + r;
+#pragma unroll
+                for (int gi = 0; gi < 8; ++gi) {
+                    const int g = blk * 8 + gi;
+                    d16[r * 8 + gi] = (n < p.N && g < p.G) ? __ldg(p.S + (size_t)n * p.G + g) : (uint16_t)0;
+                }
+            }
+            mbar_arrive(smem_u32(&ctl->sc_full[slot]));
+        }
+        last_blk = blk;
+        ++nb;
+    };
+
     if (warp == kProducerWarp) {
         // =============================== TMA producer ===============================
-        // Weights and scale blocks by TMA.  Both are static data: nothing here waits for the previous kernel.
+        // Packed weights by TMA, one 128-row x 64-k box per stage.  Static data: nothing here waits for the previous kernel.
         if (rg.it1 > rg.it0) {
             const uint64_t pol_w = policy_evict_first();
             const int n_it = rg.it1 - rg.it0;
@@ -366,39 +404,9 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
             int k = rg.it0 - tile * p.k_iters;
             int stage = 0;
             uint32_t ephase = 1;           // parity to wait on `empty` (first pass: free)
-            int nb = 0;                    // scale blocks issued
-            int last_blk = -1;
             DPROF_DECL(pw_sc = 0, pw_empty = 0, pw_w = 0, pw_a = 0);
             DPROF_T0(pt);
             for (int i = 0; i < n_it; ++i) {
-                const int blk = (k >> p.gshift) >> 3;
-                if (blk != last_blk) {
-                    const int slot = nb % kScSlots;
-                    const uint32_t par = ((nb / kScSlots) & 1) ^ 1u;
-                    wait(smem_u32(&ctl->sc_empty[slot]), par, p, DSITE_SCEMPTY);
-                    const uint32_t dst = sc_smem + slot * kScBytes;
-                    if (p.tma_scales) {
-                        if (elect_one()) {
-                            mbar_arrive_expect_tx(smem_u32(&ctl->sc_full[slot]), kScBytes);
-                            tma_load_3d_nohint(dst, &tmap_s, smem_u32(&ctl->sc_full[slot]), blk * 8, 0, tile * (TN / 256));
-                        }
-                        __syncwarp();
-                    } else {
-                        uint16_t* d16 = reinterpret_cast<uint16_t*>(smem_gen + (dst - smem_base));
-                        for (int r = lane; r < TN; r += 32) {
-                            const int n = tile * TN + r;
-#pragma unroll
-                            for (int gi = 0; gi < 8; ++gi) {
-                                const int g = blk * 8 + gi;
-                                d16[r * 8 + gi] = (n < p.N && g < p.G) ? __ldg(p.S + (size_t)n * p.G + g) : (uint16_t)0;
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_full[slot]));
-                    }
-                    last_blk = blk;
-                    ++nb;
-                }
                 DPROF_ADD(pw_sc, pt);
                 wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
                 DPROF_ADD(pw_empty, pt);
@@ -411,7 +419,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
                 DPROF_ADD(pw_w, pt);
                 DPROF_ADD(pw_a, pt);
                 if (++stage == p.stages) { stage = 0; ephase ^= 1u; }
-                if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
+                if (++k == p.k_iters) { k = 0; ++tile; }
             }
             if (lane == 0) { DPROF_OUT(8, pw_sc); DPROF_OUT(9, pw_empty); DPROF_OUT(10, pw_w); DPROF_OUT(11, pw_a); DPROF_OUT(12, n_it); }
         }
@@ -507,13 +515,16 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
-            const int tile0 = rg.it0 / p.k_iters;
-            int k = rg.it0 - tile0 * p.k_iters;
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
+            int nb = 0;                    // scale blocks issued
+            int last_blk = -1;
             const int r0 = lane >> 3, c16 = lane & 7;          // this lane's row (mod 4) and 16-byte chunk
             const uint8_t* a_lane = reinterpret_cast<const uint8_t*>(p.A) + c16 * 16;
             for (int i = 0; i < n_it; ++i) {
+                if (!has_scale_warp(MC)) scale_step(tile, k, nb, last_blk);
                 wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
                 const uint32_t bt = ring + stage * kStageBytes + kWBytes;
 #pragma unroll
@@ -534,7 +545,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
                     if (++astage == p.stages) astage = 0;
                 }
                 if (++stage == p.stages) { stage = 0; ephase ^= 1u; }
-                if (++k == p.k_iters) k = 0;
+                if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -542,6 +553,18 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w,
             for (int i = max(0, n_it - D); i < n_it; ++i) {
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->full[astage]));
                 if (++astage == p.stages) astage = 0;
+            }
+        }
+    } else if (has_scale_warp(MC) && warp == kScaleWarp) {
+        // =============================== scale blocks ===============================
+        if (rg.it1 > rg.it0) {
+            const int n_it = rg.it1 - rg.it0;
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
+            int nb = 0, last_blk = -1;
+            for (int i = 0; i < n_it; ++i) {
+                scale_step(tile, k, nb, last_blk);
+                if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
             }
         }
     } else if (warp >= kApplyWarp0) {
@@ -824,7 +847,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.k_iters = a.K / 64;
     p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
     p.ablate = a.ablate;
-    p.tma_scales = ((p.G % 8) == 0 && (a.N % 256) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;
+    p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
 
     const uint32_t fixed = kScSlots * TN * 16 + F::LUTN * kLutStride + sizeof(Ctl) + 1024 /*alignment slack*/;
     const uint32_t smem_budget = 232448u;
@@ -846,20 +869,11 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     const size_t need = kCounterBytes + (size_t)p.n_tiles * F::NJ * kMb * 128 * 4;
     if ((size_t)p.n_tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
 
-    CUtensorMap tm_w, tm_s;
+    CUtensorMap tm_w;
     const uint64_t P = (uint64_t)a.N / 16 * BITS;
     int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, 64, 128,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
-    if (p.tma_scales) {
-        // S[N, G] viewed as [N/256][256][G]: one box = 8 groups x 256 rows x (TN/256) row blocks = one scale block
-        rc = make_tmap_3d(&tm_s, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.S, (uint64_t)p.G, 256, (uint64_t)a.N / 256, (uint64_t)p.G * 2,
-                          (uint64_t)p.G * 2 * 256, 8, 256, TN / 256, CU_TENSOR_MAP_SWIZZLE_NONE);
-        if (rc != FB_OK) return rc;
-    } else {
-        tm_s = tm_w;   // unused
-    }
-
     auto kern = qgemm_decode_kernel<BITS, BF16, MC>;
     static bool attr_set[64] = {};
     if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
@@ -883,7 +897,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     }
     cfg.attrs = attrs;
     cfg.numAttrs = nattr;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, tm_s, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, p);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return FB_ERR_LAUNCH;

@@ -1,0 +1,643 @@
+// Prefill-shaped LUT-quantized GEMM for sm_100a (M > 16, 4-bit):
+//   D[M,N] = A[M,K] . W_hat[K,N],   W_hat[k,n] = round_T(table2[code(k/2,n)].{lo,hi} * S[n, k/group])
+//
+// Same role as the reference's large-M templates (flute/csrc/qgemm_kernel.hpp:24-939, config.hpp:238-325) and
+// the same dequantisation arithmetic (one multiply in T, rounded to T, before the MMA:
+// packbits_utils.hpp:105,139).  Structure shared with the decode kernel (qgemm_decode_sm100.cu): weights are
+// the tcgen05 "A" operand in TENSOR MEMORY (TMEM lane = packed row, so every field of every loaded word is
+// used), activations the "B" operand in shared memory, all dequantiser warps convert quarter-row pieces of
+// the same 64-k stage, two warp sets one stage apart.  Differences from decode:
+//   * the group scale is multiplied in while dequantising (one fma.rn.{f16,bf16}x2 per pair): with 64
+//     activation rows per tile the per-weight cost is amortised 64x, and the result is bit-identical to the
+//     reference's W_hat;
+//   * fp32 accumulators for a whole (128 packed rows x 4 fields) x 64 activation-row tile live in TMEM
+//     (4 x 64 columns) across the K loop; tcgen05.mma N = 64 runs at the full tensor rate with the A operand
+//     in TMEM (32.6 cycles per 128x64x16, measured: tools/mma_rate_probe.cu);
+//   * activations arrive by TMA (64 rows x 64 k per stage).
+//
+// Warp roles (608 threads, 1 CTA/SM, persistent):
+//   warps 0-15   dequantisers: all on the same stage (2 quads of the row per warp), double-buffered against the
+//                MMAs through two TMEM A slots; at the end of a tile the same warps run the epilogue
+//                (TMEM -> T -> D, or fp32 partials + last-arriver fix-up): warp w owns field w/4, lane quarter w%4
+//   warp  16     TMA producer (weights + activations per stage)
+//   warp  17     tcgen05.mma issuer, TMEM allocator
+//   warp  18     scale blocks ([tile columns] x [8 groups]) by cp.async
+#include "ptx.cuh"
+#include "qgemm_sm100.h"
+
+#include <cuda.h>
+
+namespace fb {
+namespace pre {
+
+#ifdef FB_PROFILE
+#define PPROF_DECL(...) long long __VA_ARGS__
+#define PPROF_T0(t) long long t = clock64()
+#define PPROF_ADD(acc, t) do { long long _n = clock64(); acc += _n - t; t = _n; } while (0)
+#define PPROF_OUT(slot, v) do { if (p.trace != nullptr) p.trace[blockIdx.x * 48 + (slot)] = (unsigned long long)(v); } while (0)
+#else
+#define PPROF_DECL(...)
+#define PPROF_T0(t)
+#define PPROF_ADD(acc, t)
+#define PPROF_OUT(slot, v)
+#endif
+
+constexpr int NJ = 4;                // pair fields per packed word (4-bit)
+constexpr int kMb = 64;              // activation rows per tile == MMA N
+constexpr int kDqWarps = 16;
+constexpr int kProducerWarp = 16;
+constexpr int kMmaWarp = 17;
+constexpr int kScaleWarp = 18;
+constexpr int kThreads = 19 * 32;
+constexpr int kMaxStages = 6;
+constexpr int kScSlots = 3;
+constexpr int kLutStride = 256;
+constexpr int kWBytes = 128 * 128;
+constexpr int kBBytes = kMb * 128;
+constexpr int kStageBytes = kWBytes + kBBytes;
+constexpr int TN = NJ * 128;
+constexpr uint32_t kScBytes = TN * 16;
+constexpr int AS = 2;                // TMEM A slots (128 columns each)
+constexpr uint32_t kDCol0 = AS * 128;
+
+struct Ctl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t a_full[AS];
+    uint64_t acc_full;
+    uint64_t acc_empty;
+    uint64_t sc_full[kScSlots];
+    uint64_t sc_empty[kScSlots];
+    uint32_t tmem_base;
+    int is_last;
+};
+
+struct Params {
+    const uint16_t* S;
+    const uint32_t* table2;
+    uint16_t* D;
+    uint8_t* workspace;
+    Diag* diag;
+    unsigned long long* trace;
+    int M, N, K, G;
+    int tile_p;
+    int gshift;
+    int n_tiles, m_tiles, k_iters;
+    int stages;
+    int streamk;
+    int tma_scales;
+    uint32_t partial_offset;
+};
+
+enum : int { PSITE_FULL = 41, PSITE_ASLOT, PSITE_ACCFULL, PSITE_SCFULL, PSITE_EMPTY, PSITE_SCEMPTY, PSITE_AFULL, PSITE_ACCEMPTY };
+
+static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t bar, uint32_t parity, int iter) {
+    if (diag != nullptr) {
+        diag->block = blockIdx.x;
+        diag->warp = threadIdx.x >> 5;
+        diag->site = site;
+        diag->index = (int)bar;
+        diag->parity = (int)parity;
+        diag->iter = iter;
+        diag->code = 1;
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const Params& p, int site, int iter = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // 4 s: trap, don't hang
+        }
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+template <int J>
+__device__ __forceinline__ uint32_t code_lane(uint32_t w, uint32_t lane4) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(lane4), "n"(0x6504 + (J << 4)));
+    return r;
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void tma_load_3d_nohint(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ int n_local(int L, int j, int tile_p) {
+    if (tile_p == 32) return (L >> 5) * (NJ * 32) + j * 32 + (L & 31);
+    return (L >> 6) * (NJ * 64) + j * 64 + (L & 63);
+}
+
+struct Range {
+    int it0, it1;
+};
+__device__ __forceinline__ Range cta_range(const Params& p, int b, int grid) {
+    Range r;
+    if (p.streamk) {
+        const int total = p.n_tiles * p.m_tiles * p.k_iters;
+        const int base = total / grid, rem = total - base * grid;
+        r.it0 = b * base + min(b, rem);
+        r.it1 = r.it0 + base + (b < rem ? 1 : 0);
+    } else {
+        const int tiles = p.n_tiles * p.m_tiles;
+        const int base = tiles / grid, rem = tiles - base * grid;
+        const int t0 = b * base + min(b, rem);
+        r.it0 = t0 * p.k_iters;
+        r.it1 = (t0 + base + (b < rem ? 1 : 0)) * p.k_iters;
+    }
+    return r;
+}
+__device__ __forceinline__ int cta_of(const Params& p, int it, int grid) {
+    const int total = p.n_tiles * p.m_tiles * p.k_iters;
+    const int base = total / grid, rem = total - base * grid;
+    const int thr = rem * (base + 1);
+    return it < thr ? it / (base + 1) : rem + (it - thr) / base;
+}
+
+// two 16-byte quads (8 consecutive k-pairs) of row L -> 4 fields x 8 TMEM columns, scaled
+template <bool BF16>
+__device__ __forceinline__ void piece(uint32_t row, int pq0, int pq1, uint32_t lut, uint32_t lane4, const uint32_t (&sc)[4],
+                                      uint32_t nz, uint32_t tcol) {
+    const uint4 v0 = lds128(row + (uint32_t)(pq0 << 4));
+    const uint4 v1 = lds128(row + (uint32_t)(pq1 << 4));
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t r[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r[0][i] = mul2<BF16>(lds32(lut + code_lane<0>(w[i], lane4)), sc[0], nz);
+        r[1][i] = mul2<BF16>(lds32(lut + code_lane<1>(w[i], lane4)), sc[1], nz);
+        r[2][i] = mul2<BF16>(lds32(lut + code_lane<2>(w[i], lane4)), sc[2], nz);
+        r[3][i] = mul2<BF16>(lds32(lut + code_lane<3>(w[i], lane4)), sc[3], nz);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * 32, r[j]);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t ring = smem_base;
+    const uint32_t sc_smem = ring + p.stages * kStageBytes;
+    const uint32_t lut = sc_smem + kScSlots * kScBytes;
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem_gen + (lut + 256 * kLutStride - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int grid = gridDim.x;
+    const Range rg = cta_range(p, blockIdx.x, grid);
+    const int spg_mask = (1 << p.gshift) - 1;
+    const int S = p.stages;
+
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 0] = globaltimer_ns();
+    pdl_wait_prior_grids();   // activations (and possibly weights) come from earlier work on the stream
+
+    if (warp == kProducerWarp && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_a);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 1);
+            mbar_init(smem_u32(&ctl->empty[s]), 1);
+        }
+        for (int s = 0; s < AS; ++s) mbar_init(smem_u32(&ctl->a_full[s]), kDqWarps);
+        mbar_init(smem_u32(&ctl->acc_full), 1);
+        mbar_init(smem_u32(&ctl->acc_empty), kDqWarps);
+        for (int s = 0; s < kScSlots; ++s) {
+            mbar_init(smem_u32(&ctl->sc_full[s]), 32);
+            mbar_init(smem_u32(&ctl->sc_empty[s]), kDqWarps);
+        }
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(smem_u32(&ctl->tmem_base), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ctl->tmem_base;
+    pdl_launch_dependents();
+
+    if (warp == kProducerWarp) {
+        // =============================== TMA producer ===============================
+        if (rg.it1 > rg.it0) {
+            const uint64_t pol_w = policy_evict_last();     // weight tiles are re-read by the other m-tiles
+            const uint64_t pol_a = policy_evict_last();
+            const int n_it = rg.it1 - rg.it0;
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
+            int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            int stage = 0;
+            uint32_t ephase = 1;
+            PPROF_DECL(pw_sc = 0, pw_empty = 0, pw_issue = 0);
+            PPROF_T0(pt);
+            for (int i = 0; i < n_it; ++i) {
+                PPROF_ADD(pw_sc, pt);
+                wait(smem_u32(&ctl->empty[stage]), ephase, p, PSITE_EMPTY);
+                PPROF_ADD(pw_empty, pt);
+                if (elect_one()) {
+                    const uint32_t bar = smem_u32(&ctl->full[stage]);
+                    mbar_arrive_expect_tx(bar, kStageBytes);
+                    tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, nt * 128, pol_w);
+                    tma_load_2d(ring + stage * kStageBytes + kWBytes, &tmap_a, bar, k * 64, mt * kMb, pol_a);
+                }
+                __syncwarp();
+                PPROF_ADD(pw_issue, pt);
+                if (++stage == S) { stage = 0; ephase ^= 1u; }
+                if (++k == p.k_iters) {
+                    k = 0;
+                    if (++mt == p.m_tiles) { mt = 0; ++nt; }
+                }
+            }
+            if (lane == 0) { PPROF_OUT(8, pw_sc); PPROF_OUT(9, pw_empty); PPROF_OUT(10, pw_issue); PPROF_OUT(12, n_it); }
+        }
+    } else if (warp == kMmaWarp) {
+        // =============================== MMA issuer =================================
+        if (rg.it1 > rg.it0) {
+            const uint32_t idesc = make_idesc_f16(BF16, 128, kMb);
+            int stage = 0;
+            int aslot = 0;
+            uint32_t aphase = 0;
+            int seg = 0;
+            PPROF_DECL(mw_acc = 0, mw_afull = 0, mw_issue = 0);
+            PPROF_T0(mt_);
+            for (int it = rg.it0; it < rg.it1;) {
+                const int tile = it / p.k_iters;
+                const int kb = it - tile * p.k_iters;
+                const int ke = min(p.k_iters, kb + (rg.it1 - it));
+                wait(smem_u32(&ctl->acc_empty), (uint32_t)(seg & 1) ^ 1u, p, PSITE_ACCEMPTY);
+                PPROF_ADD(mw_acc, mt_);
+                for (int k = kb; k < ke; ++k) {
+                    const uint64_t bdesc = make_smem_desc_sw128(ring + stage * kStageBytes + kWBytes);
+                    wait(smem_u32(&ctl->a_full[aslot]), aphase, p, PSITE_AFULL);
+                    PPROF_ADD(mw_afull, mt_);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_base = tmem + aslot * 128;
+                        const uint32_t d_base = tmem + kDCol0;
+                        const uint32_t first = (k == kb) ? 0u : 1u;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                tc_mma_ts(d_base + j * kMb, a_base + j * 32 + kk * 8, bdesc + (uint64_t)((kk * 32) >> 4), idesc,
+                                          kk == 0 ? first : 1u);
+                        }
+                        tc_commit(smem_u32(&ctl->empty[stage]));
+                        if (k == ke - 1) tc_commit(smem_u32(&ctl->acc_full));
+                    }
+                    __syncwarp();
+                    if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                    if (++stage == S) stage = 0;
+                    PPROF_ADD(mw_issue, mt_);
+                }
+                it += ke - kb;
+                ++seg;
+            }
+            if (lane == 0) { PPROF_OUT(13, mw_acc); PPROF_OUT(14, mw_afull); PPROF_OUT(16, mw_issue); }
+        }
+    } else if (warp == kScaleWarp) {
+        // =============================== scale blocks ===============================
+        if (rg.it1 > rg.it0) {
+            const int n_it = rg.it1 - rg.it0;
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
+            int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            int nb = 0;
+            int last_blk = -1;
+            for (int i = 0; i < n_it; ++i) {
+                const int blk = (k >> p.gshift) >> 3;
+                if (blk != last_blk) {
+                    const int slot = nb % kScSlots;
+                    const uint32_t par = ((nb / kScSlots) & 1) ^ 1u;
+                    wait(smem_u32(&ctl->sc_empty[slot]), par, p, PSITE_SCEMPTY);
+                    const uint32_t dst = sc_smem + slot * kScBytes;
+                    if (p.tma_scales) {
+#pragma unroll 4
+                        for (int r = lane; r < TN; r += 32) {
+                            const int n = nt * TN + r;
+                            if (n < p.N) {
+                                const uint16_t* src = p.S + (size_t)n * p.G + blk * 8;
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 16), "l"(src) : "memory");
+                            }
+                        }
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->sc_full[slot])) : "memory");
+                    } else {
+                        uint16_t* d16 = reinterpret_cast<uint16_t*>(smem_gen + (dst - smem_base));
+                        for (int r = lane; r < TN; r += 32) {
+                            const int n = nt * TN + r;
+#pragma unroll
+                            for (int gi = 0; gi < 8; ++gi) {
+                                const int g = blk * 8 + gi;
+                                d16[r * 8 + gi] = (n < p.N && g < p.G) ? __ldg(p.S + (size_t)n * p.G + g) : (uint16_t)0;
+                            }
+                        }
+                        mbar_arrive(smem_u32(&ctl->sc_full[slot]));
+                    }
+                    last_blk = blk;
+                    ++nb;
+                }
+                if (++k == p.k_iters) {
+                    k = 0;
+                    last_blk = -1;
+                    if (++mt == p.m_tiles) { mt = 0; ++nt; }
+                }
+            }
+        }
+    } else {
+        // ========================= dequantisers + epilogue ==========================
+        const int q = warp & 3;
+        const int sw = warp >> 2;               // quads 2*sw, 2*sw+1 of the row; field sw in the epilogue
+        const int L = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t lane4 = (uint32_t)lane * 4;
+        {   // lane-replicated LUT: entry e for lane l at lut + e*256 + l*4
+            uint32_t* lut_gen = reinterpret_cast<uint32_t*>(smem_gen + (lut - smem_base));
+            const int t = threadIdx.x;      // 0..511
+            const uint32_t v = __ldg(p.table2 + (t & 255));
+            const int half = t >> 8;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) lut_gen[(t & 255) * (kLutStride / 4) + half * 16 + l] = v;
+            asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
+        }
+        int nloc[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) nloc[j] = n_local(L, j, p.tile_p);
+        const uint32_t wrow = (uint32_t)L * 128;
+        const int xq = L & 7;
+        const uint32_t nz = neg_zero2();
+
+        int sc_idx = 0;
+        uint32_t sc_par = 0;
+        int stage = 0;
+        uint32_t fphase = 0;
+        int tstage = 0;                    // stage i - AS: its completion frees this stage's A slot
+        uint32_t tphase = 0;
+        int i = 0;                         // CTA-local stage counter
+        int seg = 0;
+        PPROF_DECL(dw_sc = 0, dw_full = 0, dw_aslot = 0, dw_piece = 0, dw_st = 0, dw_epiw = 0, dw_epi = 0);
+        PPROF_T0(dt);
+        for (int it = rg.it0; it < rg.it1;) {
+            const int tile = it / p.k_iters;
+            const int kb = it - tile * p.k_iters;
+            const int ke = min(p.k_iters, kb + (rg.it1 - it));
+            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            int cur_blk = -1;
+            int sc_g = -1;
+            uint32_t sc[4] = {0, 0, 0, 0};
+            for (int k = kb; k < ke; ++k, ++i) {
+                const int g = k >> p.gshift;
+                if ((g >> 3) != cur_blk) {
+                    if (cur_blk >= 0) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[sc_idx]));
+                        if (++sc_idx == kScSlots) { sc_idx = 0; sc_par ^= 1u; }
+                    }
+                    cur_blk = g >> 3;
+                    wait(smem_u32(&ctl->sc_full[sc_idx]), sc_par, p, PSITE_SCFULL);
+                }
+                if (g != sc_g) {
+                    const uint32_t sc_base = sc_smem + sc_idx * kScBytes + (g & 7) * 2;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const uint32_t s16 = lds16(sc_base + nloc[j] * 16);
+                        sc[j] = s16 | (s16 << 16);
+                    }
+                    sc_g = g;
+                }
+                PPROF_ADD(dw_sc, dt);
+                wait(smem_u32(&ctl->full[stage]), fphase, p, PSITE_FULL);
+                PPROF_ADD(dw_full, dt);
+                if (i >= AS) {
+                    wait(smem_u32(&ctl->empty[tstage]), tphase, p, PSITE_ASLOT, i);
+                    if (++tstage == S) { tstage = 0; tphase ^= 1u; }
+                }
+                PPROF_ADD(dw_aslot, dt);
+                tc_fence_after();
+                const uint32_t row = ring + stage * kStageBytes + wrow;
+                const int aslot = i & 1;
+                piece<BF16>(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, sc, nz, tmem + lane_sel + aslot * 128 + sw * 8);
+                PPROF_ADD(dw_piece, dt);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
+                if (++stage == S) { stage = 0; fphase ^= 1u; }
+                PPROF_ADD(dw_st, dt);
+            }
+            if (cur_blk >= 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[sc_idx]));
+                if (++sc_idx == kScSlots) { sc_idx = 0; sc_par ^= 1u; }
+            }
+
+            // ------------------------------- epilogue: field sw, lane quarter q ----------------------
+            wait(smem_u32(&ctl->acc_full), (uint32_t)(seg & 1), p, PSITE_ACCFULL);
+            tc_fence_after();
+            PPROF_ADD(dw_epiw, dt);
+            const bool full_k = (kb == 0) && (ke == p.k_iters);
+            const int m_base = mt * kMb;
+            const int n = nt * TN + n_local(L, sw, p.tile_p);
+            const int rows_valid = min(kMb, p.M - m_base);
+            float* accum = nullptr;
+            int contributors = 1;
+            if (!full_k) {
+                const int tile_it0 = tile * p.k_iters;
+                const int first_cta = cta_of(p, tile_it0, grid);
+                contributors = cta_of(p, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
+                accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
+            }
+#pragma unroll 1
+            for (int mc = 0; mc < rows_valid; mc += 16) {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tmem + lane_sel + kDCol0 + sw * kMb + mc, r);
+                tc_wait_ld();
+                if (full_k) {
+                    if (n < p.N) {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x)
+                            if (mc + x < rows_valid) p.D[(size_t)(m_base + mc + x) * p.N + n] = f32_to_t<BF16>(__uint_as_float(r[x]));
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 16; ++x)
+                        if (mc + x < rows_valid) red_add_f32(accum + (sw * kMb + mc + x) * 128 + L, __uint_as_float(r[x]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
+            if (!full_k) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
+                if (threadIdx.x == 0) {
+                    const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
+                    const int last = (old == contributors - 1) ? 1 : 0;
+                    if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;
+                    ctl->is_last = last;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
+                if (ctl->is_last) {
+                    for (int mi = 0; mi < rows_valid; ++mi) {
+                        float* src = accum + (sw * kMb + mi) * 128 + L;
+                        const float v = __ldcg(src);
+                        *src = 0.f;
+                        if (n < p.N) p.D[(size_t)(m_base + mi) * p.N + n] = f32_to_t<BF16>(v);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
+            }
+            PPROF_ADD(dw_epi, dt);
+            it += ke - kb;
+            ++seg;
+        }
+#ifdef FB_PROFILE
+        if (lane == 0 && (warp == 0 || warp == 9)) {
+            const int o = (warp == 0) ? 24 : 32;
+            PPROF_OUT(o + 0, dw_full); PPROF_OUT(o + 1, dw_aslot); PPROF_OUT(o + 2, dw_piece); PPROF_OUT(o + 3, dw_st); PPROF_OUT(o + 4, dw_sc);
+            PPROF_OUT(o + 5, dw_epiw); PPROF_OUT(o + 6, dw_epi);
+        }
+#endif
+    }
+
+    // ---- teardown ------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 7] = globaltimer_ns();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+template <bool BF16>
+static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
+    Params p{};
+    p.S = static_cast<const uint16_t*>(a.S);
+    p.table2 = static_cast<const uint32_t*>(a.table2);
+    p.D = static_cast<uint16_t*>(a.D);
+    p.workspace = static_cast<uint8_t*>(a.workspace);
+    p.diag = a.diag;
+    p.trace = a.trace;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.G = a.K / a.group_size;
+    p.tile_p = a.tile_p;
+    p.gshift = (a.group_size == 64) ? 0 : (a.group_size == 128) ? 1 : 2;
+    p.n_tiles = (a.N + TN - 1) / TN;
+    p.m_tiles = (a.M + kMb - 1) / kMb;
+    p.k_iters = a.K / 64;
+    p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows: cp.async
+
+    const uint32_t fixed = kScSlots * kScBytes + 256 * kLutStride + sizeof(Ctl) + 1024;
+    const uint32_t smem_budget = 232448u;
+    int stages = (int)((smem_budget - fixed) / kStageBytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
+    if (stages < 2) return FB_ERR_INTERNAL;
+    p.stages = stages;
+    const uint32_t smem_bytes = stages * kStageBytes + fixed;
+
+    const long long tiles = (long long)p.n_tiles * p.m_tiles;
+    const long long total = tiles * p.k_iters;
+    if (total > 0x3fffffffLL || tiles >= (1 << 19)) return FB_ERR_SHAPE;
+    int grid = a.num_sms;
+    if (a.force_grid > 0) grid = a.force_grid;
+    p.streamk = (tiles < 4LL * grid) ? 1 : 0;
+    if (a.force_streamk >= 0) p.streamk = a.force_streamk;
+    if (p.streamk) { if (grid > total) grid = (int)total; }
+    else           { if (grid > tiles) grid = (int)tiles; }
+
+    constexpr size_t kCounterBytes = 65536;
+    p.partial_offset = (uint32_t)kCounterBytes;
+    if (p.streamk) {
+        const size_t need = kCounterBytes + (size_t)tiles * NJ * kMb * 128 * 4;
+        if ((size_t)tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
+    }
+
+    CUtensorMap tm_w, tm_a;
+    const uint64_t P = (uint64_t)a.N / 16 * 4;
+    int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, 64, 128,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FB_OK) return rc;
+    rc = make_tmap_2d(&tm_a, BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.A, (uint64_t)a.K,
+                      (uint64_t)a.M, (uint64_t)a.K * 2, 64, kMb, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FB_OK) return rc;
+    auto kern = qgemm_prefill_kernel<BF16>;
+    static bool attr_set[64] = {};
+    if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
+            cudaGetLastError();
+            return FB_ERR_LAUNCH;
+        }
+        attr_set[a.device] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    int nattr = 0;
+    if (a.flags & FB_FLAG_PDL) {
+        attrs[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = nattr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, tm_a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_LAUNCH;
+    }
+    return FB_OK;
+}
+
+}  // namespace pre
+
+bool qgemm_prefill_supported(const QgemmArgs& a) { return a.num_bits == 4 && a.M > 16; }
+
+int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream) {
+    return a.bf16 ? pre::launch_t<true>(a, stream) : pre::launch_t<false>(a, stream);
+}
+
+}  // namespace fb

@@ -69,6 +69,9 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);
 // decode-shaped kernel (M <= 16, 2/4-bit): qgemm_decode_sm100.cu
 bool qgemm_decode_supported(const QgemmArgs& a);
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream);
+// prefill-shaped kernel (M > 16, 4-bit): qgemm_prefill_sm100.cu
+bool qgemm_prefill_supported(const QgemmArgs& a);
+int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream);
 int qgemm_max_mb(int bits);
 int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                  uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);

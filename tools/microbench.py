@@ -101,6 +101,15 @@ def main():
                     for c, nm in prof:
                         col = t[:, c]
                         print(f"     {nm:26s} min {col.min():8d} med {int(np.median(col)):8d} max {col.max():8d}")
+                elif os.environ.get("FLUTE_B200_PROFILE") == "1" and bits == 4 and args.variant < 0:
+                    prof = [(8, "producer scale blocks"), (9, "producer wait-empty"), (10, "producer issue"), (12, "producer iters"),
+                            (13, "mma wait-accempty"), (14, "mma wait-afull"), (16, "mma issue+commit"),
+                            (24, "dq0 wait-full"), (25, "dq0 wait-aslot"), (26, "dq0 pieces"), (27, "dq0 wait-st+arrive"), (28, "dq0 scales+loop"),
+                            (32, "dq9 wait-full"), (33, "dq9 wait-aslot"), (34, "dq9 pieces"), (35, "dq9 wait-st+arrive"), (36, "dq9 scales+loop"),
+                            (29, "dq0 epilogue wait"), (30, "dq0 epilogue work"), (37, "dq9 epilogue wait"), (38, "dq9 epilogue work")]
+                    for c, nm in prof:
+                        col = t[:, c]
+                        print(f"     {nm:26s} min {col.min():8d} med {int(np.median(col)):8d} max {col.max():8d}")
                 elif os.environ.get("FLUTE_B200_PROFILE") == "1":
                     prof = [(8, "producer wait-empty"), (9, "producer issue"), (10, "producer iters"), (11, "mma wait-full"),
                             (12, "mma wait-afull"), (13, "mma issue+commit"), (14, "mma wait-accempty"),
