@@ -315,7 +315,7 @@ def run_own(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": peak_kind, "traffic": traffic,
                          "algorithmic_bytes_per_launch_avg": nbytes / launches_per_step,
-                         "kernel": "fb::qgemm_sm100_kernel<4,true>"},
+                         "kernel": "fb::dec::qgemm_decode_kernel<4,true,1>"},
             "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": x_host.numel() * 2,
                     "d2h_bytes_per_step": y_host.numel() * 2,
                     "api": "flute_b200.qgemm_simple (torch op) x128 in one CUDA graph + pinned H2D/D2H, host sync per step"},

@@ -867,7 +867,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     constexpr size_t kCounterBytes = 65536;
     p.partial_offset = (uint32_t)kCounterBytes;
     const size_t need = kCounterBytes + (size_t)p.n_tiles * F::NJ * kMb * 128 * 4;
-    if ((size_t)p.n_tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
+    if ((size_t)p.n_tiles * 4 > kCounterBytes || need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
 
     CUtensorMap tm_w;
     const uint64_t P = (uint64_t)a.N / 16 * BITS;

@@ -4,21 +4,25 @@
 // Same role as the reference's large-M templates (flute/csrc/qgemm_kernel.hpp:24-939, config.hpp:238-325) and
 // the same dequantisation arithmetic (one multiply in T, rounded to T, before the MMA:
 // packbits_utils.hpp:105,139).  Structure shared with the decode kernel (qgemm_decode_sm100.cu): weights are
-// the tcgen05 "A" operand in TENSOR MEMORY (TMEM lane = packed row, so every field of every loaded word is
-// used), activations the "B" operand in shared memory, all dequantiser warps convert quarter-row pieces of
-// the same 64-k stage, two warp sets one stage apart.  Differences from decode:
-//   * the group scale is multiplied in while dequantising (one fma.rn.{f16,bf16}x2 per pair): with 64
-//     activation rows per tile the per-weight cost is amortised 64x, and the result is bit-identical to the
-//     reference's W_hat;
-//   * fp32 accumulators for a whole (128 packed rows x 4 fields) x 64 activation-row tile live in TMEM
-//     (4 x 64 columns) across the K loop; tcgen05.mma N = 64 runs at the full tensor rate with the A operand
-//     in TMEM (32.6 cycles per 128x64x16, measured: tools/mma_rate_probe.cu);
-//   * activations arrive by TMA (64 rows x 64 k per stage).
+// the tcgen05 "A" operand in TENSOR MEMORY (TMEM lane = packed row), activations the "B" operand in shared
+// memory, all 16 dequantiser warps convert quarter-row pieces of the same 64-k stage.  Differences:
+//   * the group scale is multiplied in while dequantising (one fma.rn.{f16,bf16}x2 per pair): bit-identical
+//     to the reference's W_hat;
+//   * a tile is 128 packed rows x TWO of the four pair fields (256 output columns) x 128 activation rows.
+//     Dequantisation is the scarce resource (measured ~540 cycles per 64-k stage for four fields against
+//     ~520 cycles of tensor work), so every dequantised weight is used for 128 rows instead of 64 and a stage
+//     converts two fields instead of four; the other field pair of the same packed rows is another tile (the
+//     packed words are fetched twice, from L2);
+//   * fp32 accumulators (2 fields x 128 columns) live in TMEM across the K loop; tcgen05.mma N = 128 runs at the
+//     full tensor rate with the A operand in TMEM (64.6 cycles per 128x128x16, tools/mma_rate_probe.cu);
+//   * activations arrive by TMA (128 rows x 64 k per stage);
+//   * a K range that does not cover a whole tile (Stream-K) is written as plain fp32 vectors to a per-CTA
+//     scratch slot and summed by the last CTA to arrive: 16K atomics per partial tile cost ~40k cycles.
 //
 // Warp roles (608 threads, 1 CTA/SM, persistent):
-//   warps 0-15   dequantisers: all on the same stage (2 quads of the row per warp), double-buffered against the
-//                MMAs through two TMEM A slots; at the end of a tile the same warps run the epilogue
-//                (TMEM -> T -> D, or fp32 partials + last-arriver fix-up): warp w owns field w/4, lane quarter w%4
+//   warps 0-15   dequantisers (2 quads of the row per warp), four TMEM A slots ahead of the MMAs; at the end of a
+//                tile the same warps run the epilogue: warp w owns field (w/4)&1, activation-row half w/8, lane
+//                quarter w%4
 //   warp  16     TMA producer (weights + activations per stage)
 //   warp  17     tcgen05.mma issuer, TMEM allocator
 //   warp  18     scale blocks ([tile columns] x [8 groups]) by cp.async
@@ -43,13 +47,14 @@ namespace pre {
 #endif
 
 constexpr int NJ = 4;                // pair fields per packed word (4-bit)
-constexpr int kMb = 64;              // activation rows per tile == MMA N
+constexpr int NF = 2;                // fields per tile
+constexpr int kMb = 128;             // activation rows per tile == MMA N
 constexpr int kDqWarps = 16;
 constexpr int kProducerWarp = 16;
 constexpr int kMmaWarp = 17;
 constexpr int kScaleWarp = 18;
 constexpr int kThreads = 19 * 32;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 4;
 constexpr int kScSlots = 3;
 constexpr int kLutStride = 256;
 constexpr int kWBytes = 128 * 128;
@@ -57,8 +62,10 @@ constexpr int kBBytes = kMb * 128;
 constexpr int kStageBytes = kWBytes + kBBytes;
 constexpr int TN = NJ * 128;
 constexpr uint32_t kScBytes = TN * 16;
-constexpr int AS = 2;                // TMEM A slots (128 columns each)
-constexpr uint32_t kDCol0 = AS * 128;
+constexpr int AS = 4;                // TMEM A slots (NF * 32 = 64 columns each)
+constexpr uint32_t kACols = NF * 32;
+constexpr uint32_t kDCol0 = AS * kACols;
+constexpr size_t kPartBytes = (size_t)NF * kMb * 128 * 4;   // one partial tile: fp32 [16 warps][32 lanes][64]
 
 struct Ctl {
     uint64_t full[kMaxStages];
@@ -86,7 +93,7 @@ struct Params {
     int stages;
     int streamk;
     int tma_scales;
-    uint32_t partial_offset;
+    size_t scratch_offset;   // per-CTA partial-tile slots (2 per CTA) at the end of the workspace
 };
 
 enum : int { PSITE_FULL = 41, PSITE_ASLOT, PSITE_ACCFULL, PSITE_SCFULL, PSITE_EMPTY, PSITE_SCEMPTY, PSITE_AFULL, PSITE_ACCEMPTY };
@@ -169,15 +176,28 @@ __device__ __forceinline__ int n_local(int L, int j, int tile_p) {
 struct Range {
     int it0, it1;
 };
+// tile -> (packed-row block nt, field pair fp, activation-row block mt); mt fastest so that consecutive tiles share W
+struct TileCoord {
+    int nt, fp, mt;
+};
+__device__ __forceinline__ TileCoord tile_coord(const Params& p, int tile) {
+    TileCoord c;
+    const int per_nt = 2 * p.m_tiles;
+    c.nt = tile / per_nt;
+    const int r = tile - c.nt * per_nt;
+    c.fp = r / p.m_tiles;
+    c.mt = r - c.fp * p.m_tiles;
+    return c;
+}
 __device__ __forceinline__ Range cta_range(const Params& p, int b, int grid) {
     Range r;
     if (p.streamk) {
-        const int total = p.n_tiles * p.m_tiles * p.k_iters;
+        const int total = p.n_tiles * 2 * p.m_tiles * p.k_iters;
         const int base = total / grid, rem = total - base * grid;
         r.it0 = b * base + min(b, rem);
         r.it1 = r.it0 + base + (b < rem ? 1 : 0);
     } else {
-        const int tiles = p.n_tiles * p.m_tiles;
+        const int tiles = p.n_tiles * 2 * p.m_tiles;
         const int base = tiles / grid, rem = tiles - base * grid;
         const int t0 = b * base + min(b, rem);
         r.it0 = t0 * p.k_iters;
@@ -186,29 +206,27 @@ __device__ __forceinline__ Range cta_range(const Params& p, int b, int grid) {
     return r;
 }
 __device__ __forceinline__ int cta_of(const Params& p, int it, int grid) {
-    const int total = p.n_tiles * p.m_tiles * p.k_iters;
+    const int total = p.n_tiles * 2 * p.m_tiles * p.k_iters;
     const int base = total / grid, rem = total - base * grid;
     const int thr = rem * (base + 1);
     return it < thr ? it / (base + 1) : rem + (it - thr) / base;
 }
 
-// two 16-byte quads (8 consecutive k-pairs) of row L -> 4 fields x 8 TMEM columns, scaled
-template <bool BF16>
-__device__ __forceinline__ void piece(uint32_t row, int pq0, int pq1, uint32_t lut, uint32_t lane4, const uint32_t (&sc)[4],
+// two 16-byte quads (8 consecutive k-pairs) of row L -> fields 2*FP, 2*FP+1 x 8 TMEM columns, scaled
+template <bool BF16, int FP>
+__device__ __forceinline__ void piece(uint32_t row, int pq0, int pq1, uint32_t lut, uint32_t lane4, const uint32_t (&sc)[2],
                                       uint32_t nz, uint32_t tcol) {
     const uint4 v0 = lds128(row + (uint32_t)(pq0 << 4));
     const uint4 v1 = lds128(row + (uint32_t)(pq1 << 4));
     const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    uint32_t r[4][8];
+    uint32_t r[2][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        r[0][i] = mul2<BF16>(lds32(lut + code_lane<0>(w[i], lane4)), sc[0], nz);
-        r[1][i] = mul2<BF16>(lds32(lut + code_lane<1>(w[i], lane4)), sc[1], nz);
-        r[2][i] = mul2<BF16>(lds32(lut + code_lane<2>(w[i], lane4)), sc[2], nz);
-        r[3][i] = mul2<BF16>(lds32(lut + code_lane<3>(w[i], lane4)), sc[3], nz);
+        r[0][i] = mul2<BF16>(lds32(lut + code_lane<2 * FP>(w[i], lane4)), sc[0], nz);
+        r[1][i] = mul2<BF16>(lds32(lut + code_lane<2 * FP + 1>(w[i], lane4)), sc[1], nz);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * 32, r[j]);
+    tmem_st_x8(tcol, r[0]);
+    tmem_st_x8(tcol + 32, r[1]);
 }
 
 template <bool BF16>
@@ -266,7 +284,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             const int n_it = rg.it1 - rg.it0;
             int tile = rg.it0 / p.k_iters;
             int k = rg.it0 - tile * p.k_iters;
-            int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            TileCoord tc = tile_coord(p, tile);
             int stage = 0;
             uint32_t ephase = 1;
             PPROF_DECL(pw_sc = 0, pw_empty = 0, pw_issue = 0);
@@ -278,15 +296,15 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 if (elect_one()) {
                     const uint32_t bar = smem_u32(&ctl->full[stage]);
                     mbar_arrive_expect_tx(bar, kStageBytes);
-                    tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, nt * 128, pol_w);
-                    tma_load_2d(ring + stage * kStageBytes + kWBytes, &tmap_a, bar, k * 64, mt * kMb, pol_a);
+                    tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, tc.nt * 128, pol_w);
+                    tma_load_2d(ring + stage * kStageBytes + kWBytes, &tmap_a, bar, k * 64, tc.mt * kMb, pol_a);
                 }
                 __syncwarp();
                 PPROF_ADD(pw_issue, pt);
                 if (++stage == S) { stage = 0; ephase ^= 1u; }
                 if (++k == p.k_iters) {
                     k = 0;
-                    if (++mt == p.m_tiles) { mt = 0; ++nt; }
+                    tc = tile_coord(p, ++tile);
                 }
             }
             if (lane == 0) { PPROF_OUT(8, pw_sc); PPROF_OUT(9, pw_empty); PPROF_OUT(10, pw_issue); PPROF_OUT(12, n_it); }
@@ -313,14 +331,14 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                     PPROF_ADD(mw_afull, mt_);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_base = tmem + aslot * 128;
+                        const uint32_t a_base = tmem + aslot * kACols;
                         const uint32_t d_base = tmem + kDCol0;
                         const uint32_t first = (k == kb) ? 0u : 1u;
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j) {
+                        for (int f = 0; f < NF; ++f) {
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk)
-                                tc_mma_ts(d_base + j * kMb, a_base + j * 32 + kk * 8, bdesc + (uint64_t)((kk * 32) >> 4), idesc,
+                                tc_mma_ts(d_base + f * kMb, a_base + f * 32 + kk * 8, bdesc + (uint64_t)((kk * 32) >> 4), idesc,
                                           kk == 0 ? first : 1u);
                         }
                         tc_commit(smem_u32(&ctl->empty[stage]));
@@ -342,7 +360,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             const int n_it = rg.it1 - rg.it0;
             int tile = rg.it0 / p.k_iters;
             int k = rg.it0 - tile * p.k_iters;
-            int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            int nt = tile_coord(p, tile).nt;
             int nb = 0;
             int last_blk = -1;
             for (int i = 0; i < n_it; ++i) {
@@ -380,7 +398,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 if (++k == p.k_iters) {
                     k = 0;
                     last_blk = -1;
-                    if (++mt == p.m_tiles) { mt = 0; ++nt; }
+                    nt = tile_coord(p, ++tile).nt;
                 }
             }
         }
@@ -400,20 +418,16 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             for (int l = 0; l < 16; ++l) lut_gen[(t & 255) * (kLutStride / 4) + half * 16 + l] = v;
             asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
         }
-        int nloc[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) nloc[j] = n_local(L, j, p.tile_p);
         const uint32_t wrow = (uint32_t)L * 128;
         const int xq = L & 7;
         const uint32_t nz = neg_zero2();
+        const int ef = sw & 1, emh = sw >> 1;          // epilogue: field of the pair, activation-row half
 
         int sc_idx = 0;
         uint32_t sc_par = 0;
         int stage = 0;
         uint32_t fphase = 0;
-        int tstage = 0;                    // stage i - AS: its completion frees this stage's A slot
-        uint32_t tphase = 0;
-        int i = 0;                         // CTA-local stage counter
+        int aslot = 0;
         int seg = 0;
         PPROF_DECL(dw_sc = 0, dw_full = 0, dw_aslot = 0, dw_piece = 0, dw_st = 0, dw_epiw = 0, dw_epi = 0);
         PPROF_T0(dt);
@@ -421,11 +435,12 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             const int tile = it / p.k_iters;
             const int kb = it - tile * p.k_iters;
             const int ke = min(p.k_iters, kb + (rg.it1 - it));
-            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+            const TileCoord tc = tile_coord(p, tile);
+            const int nl0 = n_local(L, 2 * tc.fp, p.tile_p), nl1 = n_local(L, 2 * tc.fp + 1, p.tile_p);
             int cur_blk = -1;
             int sc_g = -1;
-            uint32_t sc[4] = {0, 0, 0, 0};
-            for (int k = kb; k < ke; ++k, ++i) {
+            uint32_t sc[2] = {0, 0};
+            for (int k = kb; k < ke; ++k) {
                 const int g = k >> p.gshift;
                 if ((g >> 3) != cur_blk) {
                     if (cur_blk >= 0) {
@@ -438,30 +453,27 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 }
                 if (g != sc_g) {
                     const uint32_t sc_base = sc_smem + sc_idx * kScBytes + (g & 7) * 2;
-#pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        const uint32_t s16 = lds16(sc_base + nloc[j] * 16);
-                        sc[j] = s16 | (s16 << 16);
-                    }
+                    const uint32_t s0 = lds16(sc_base + nl0 * 16), s1 = lds16(sc_base + nl1 * 16);
+                    sc[0] = s0 | (s0 << 16);
+                    sc[1] = s1 | (s1 << 16);
                     sc_g = g;
                 }
                 PPROF_ADD(dw_sc, dt);
+                // (the stage's A slot is free as soon as its data has landed: with as many A slots as ring stages the
+                // producer could only refill this stage after the MMAs that read slot `aslot` four stages ago completed)
                 wait(smem_u32(&ctl->full[stage]), fphase, p, PSITE_FULL);
                 PPROF_ADD(dw_full, dt);
-                if (i >= AS) {
-                    wait(smem_u32(&ctl->empty[tstage]), tphase, p, PSITE_ASLOT, i);
-                    if (++tstage == S) { tstage = 0; tphase ^= 1u; }
-                }
-                PPROF_ADD(dw_aslot, dt);
                 tc_fence_after();
                 const uint32_t row = ring + stage * kStageBytes + wrow;
-                const int aslot = i & 1;
-                piece<BF16>(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, sc, nz, tmem + lane_sel + aslot * 128 + sw * 8);
+                const uint32_t tcol = tmem + lane_sel + aslot * kACols + sw * 8;
+                if (tc.fp == 0) piece<BF16, 0>(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, sc, nz, tcol);
+                else piece<BF16, 1>(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, sc, nz, tcol);
                 PPROF_ADD(dw_piece, dt);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
+                if (++aslot == AS) aslot = 0;
                 if (++stage == S) { stage = 0; fphase ^= 1u; }
                 PPROF_ADD(dw_st, dt);
             }
@@ -471,60 +483,88 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 if (++sc_idx == kScSlots) { sc_idx = 0; sc_par ^= 1u; }
             }
 
-            // ------------------------------- epilogue: field sw, lane quarter q ----------------------
+            // ---------------- epilogue: field ef of the pair, rows [emh*64, emh*64+64), lane quarter q ----------------
             wait(smem_u32(&ctl->acc_full), (uint32_t)(seg & 1), p, PSITE_ACCFULL);
             tc_fence_after();
             PPROF_ADD(dw_epiw, dt);
             const bool full_k = (kb == 0) && (ke == p.k_iters);
-            const int m_base = mt * kMb;
-            const int n = nt * TN + n_local(L, sw, p.tile_p);
-            const int rows_valid = min(kMb, p.M - m_base);
-            float* accum = nullptr;
-            int contributors = 1;
-            if (!full_k) {
-                const int tile_it0 = tile * p.k_iters;
-                const int first_cta = cta_of(p, tile_it0, grid);
-                contributors = cta_of(p, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
-                accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
-            }
+            const int m0 = tc.mt * kMb + emh * 64;
+            const int n = tc.nt * TN + (ef ? nl1 : nl0);
+            const int rows_valid = min(64, p.M - m0);     // may be <= 0
+            const uint32_t dcol = tmem + lane_sel + kDCol0 + ef * kMb + emh * 64;
+            if (full_k) {
 #pragma unroll 1
-            for (int mc = 0; mc < rows_valid; mc += 16) {
-                uint32_t r[16];
-                tmem_ld_32x32b_x16(tmem + lane_sel + kDCol0 + sw * kMb + mc, r);
-                tc_wait_ld();
-                if (full_k) {
+                for (int mc = 0; mc < rows_valid; mc += 16) {
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(dcol + mc, r);
+                    tc_wait_ld();
                     if (n < p.N) {
 #pragma unroll
                         for (int x = 0; x < 16; ++x)
-                            if (mc + x < rows_valid) p.D[(size_t)(m_base + mc + x) * p.N + n] = f32_to_t<BF16>(__uint_as_float(r[x]));
+                            if (mc + x < rows_valid) p.D[(size_t)(m0 + mc + x) * p.N + n] = f32_to_t<BF16>(__uint_as_float(r[x]));
                     }
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 16; ++x)
-                        if (mc + x < rows_valid) red_add_f32(accum + (sw * kMb + mc + x) * 128 + L, __uint_as_float(r[x]));
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
-            if (!full_k) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
+            } else {
+                // Partial K range.  This CTA's partial tile goes to one of its two scratch slots (slot 0: the
+                // segment starts at the CTA's first stage; slot 1: the CTA's last segment) as 64 consecutive floats
+                // per thread; the CTA that arrives last on the tile's counter sums every contributor's slot.
+                const int tile_it0 = tile * p.k_iters;
+                const int first_cta = cta_of(p, tile_it0, grid);
+                const int last_cta = cta_of(p, tile_it0 + p.k_iters - 1, grid);
+                float* scratch = reinterpret_cast<float*>(p.workspace + p.scratch_offset);
+                const size_t part_floats = kPartBytes / 4;
+                const size_t my_off = (size_t)(warp * 32 + lane) * 64;
+                {
+                    float* dst = scratch + ((size_t)blockIdx.x * 2 + (it == rg.it0 ? 0 : 1)) * part_floats + my_off;
+#pragma unroll 1
+                    for (int mc = 0; mc < 64; mc += 16) {
+                        uint32_t r[16];
+                        tmem_ld_32x32b_x16(dcol + mc, r);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int x = 0; x < 16; x += 4)
+                            __stcg(reinterpret_cast<uint4*>(dst + mc + x), make_uint4(r[x], r[x + 1], r[x + 2], r[x + 3]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
+                __threadfence();
                 asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
                 if (threadIdx.x == 0) {
                     const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
-                    const int last = (old == contributors - 1) ? 1 : 0;
+                    const int last = (old == last_cta - first_cta) ? 1 : 0;
                     if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;
                     ctl->is_last = last;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
                 if (ctl->is_last) {
-                    for (int mi = 0; mi < rows_valid; ++mi) {
-                        float* src = accum + (sw * kMb + mi) * 128 + L;
-                        const float v = __ldcg(src);
-                        *src = 0.f;
-                        if (n < p.N) p.D[(size_t)(m_base + mi) * p.N + n] = f32_to_t<BF16>(v);
+                    __threadfence();
+#pragma unroll 1
+                    for (int mc = 0; mc < rows_valid; mc += 16) {
+                        float acc[16];
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) acc[x] = 0.f;
+                        for (int c = first_cta; c <= last_cta; ++c) {
+                            const Range rc = cta_range(p, c, grid);
+                            const float* src = scratch + ((size_t)c * 2 + (rc.it0 >= tile_it0 ? 0 : 1)) * part_floats + my_off + mc;
+#pragma unroll
+                            for (int x = 0; x < 16; x += 4) {
+                                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + x));
+                                acc[x] += v.x; acc[x + 1] += v.y; acc[x + 2] += v.z; acc[x + 3] += v.w;
+                            }
+                        }
+                        if (n < p.N) {
+#pragma unroll
+                            for (int x = 0; x < 16; ++x)
+                                if (mc + x < rows_valid) p.D[(size_t)(m0 + mc + x) * p.N + n] = f32_to_t<BF16>(acc[x]);
+                        }
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");   // is_last is reused by the next segment
             }
             PPROF_ADD(dw_epi, dt);
             it += ke - kb;
@@ -576,22 +616,26 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.stages = stages;
     const uint32_t smem_bytes = stages * kStageBytes + fixed;
 
-    const long long tiles = (long long)p.n_tiles * p.m_tiles;
+    const long long tiles = (long long)p.n_tiles * 2 * p.m_tiles;
     const long long total = tiles * p.k_iters;
     if (total > 0x3fffffffLL || tiles >= (1 << 19)) return FB_ERR_SHAPE;
     int grid = a.num_sms;
     if (a.force_grid > 0) grid = a.force_grid;
-    p.streamk = (tiles < 4LL * grid) ? 1 : 0;
+    // whole tiles per CTA unless that leaves more than ~10 % of the machine idle in the last wave
+    {
+        const long long waves = (tiles + grid - 1) / grid;
+        p.streamk = (tiles * 10 < waves * grid * 9) ? 1 : 0;
+    }
     if (a.force_streamk >= 0) p.streamk = a.force_streamk;
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
 
+    // workspace: [tile counters: fixed 64 KB, zero between launches][... zero-invariant fp32 accumulators of the
+    // other kernels ...][2 partial-tile slots per CTA at the very end, contents undefined between launches]
     constexpr size_t kCounterBytes = 65536;
-    p.partial_offset = (uint32_t)kCounterBytes;
-    if (p.streamk) {
-        const size_t need = kCounterBytes + (size_t)tiles * NJ * kMb * 128 * 4;
-        if ((size_t)tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
-    }
+    const size_t scratch = prefill_scratch_bytes(a.num_sms);
+    if ((size_t)tiles * 4 > kCounterBytes || a.workspace_bytes < kCounterBytes + scratch || grid > a.num_sms) return FB_ERR_WORKSPACE;
+    p.scratch_offset = (a.workspace_bytes - scratch) & ~(size_t)255;
 
     CUtensorMap tm_w, tm_a;
     const uint64_t P = (uint64_t)a.N / 16 * 4;

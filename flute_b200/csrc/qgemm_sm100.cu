@@ -992,7 +992,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.partial_offset = (uint32_t)kCounterBytes;
     if (p.streamk) {
         const size_t need = kCounterBytes + (size_t)tiles * F::NJ * mb * 128 * 4;
-        if ((size_t)tiles * 4 > kCounterBytes || need > a.workspace_bytes) return FB_ERR_WORKSPACE;
+        if ((size_t)tiles * 4 > kCounterBytes || need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
     }
 
     CUtensorMap tm_w, tm_a;

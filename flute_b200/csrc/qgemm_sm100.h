@@ -70,6 +70,9 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);
 bool qgemm_decode_supported(const QgemmArgs& a);
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream);
 // prefill-shaped kernel (M > 16, 4-bit): qgemm_prefill_sm100.cu
+// The tail of the workspace holds its per-CTA partial-tile slots (2 x 128 KB per SM, contents undefined between
+// launches); the zero-invariant fp32 accumulators of the other kernels must stay below it.
+inline size_t prefill_scratch_bytes(int num_sms) { return (size_t)num_sms * 2 * 131072 + 256; }
 bool qgemm_prefill_supported(const QgemmArgs& a);
 int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream);
 int qgemm_max_mb(int bits);

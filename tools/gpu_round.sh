@@ -25,11 +25,11 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 128 -c 128 --csv \
       --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/ncu_launch.log" 2>&1
   # full capture: gate_up (28672x4096), o (4096x4096) decode launches of the second eager token
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:qgemm_sm100 -s 129 -c 2 \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:qgemm_decode -s 129 -c 2 \
       -o "$OUT/prof_decode" -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
   tail -2 "$OUT/ncu_full.log"
   if [ "${NCU_PREFILL:-1}" = "1" ]; then
-    timeout 300 ncu --set full --clock-control none --import-source on -k regex:qgemm_sm100 -s 2 -c 1 \
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:qgemm_prefill -s 2 -c 1 \
         -o "$OUT/prof_prefill" -f python tools/microbench.py --M 4096 --shapes small --reps 1 > "$OUT/ncu_prefill.log" 2>&1
     tail -2 "$OUT/ncu_prefill.log"
   fi
