@@ -163,6 +163,56 @@ def test_schedules_agree(force, dev, ws):
     assert_close(run_cabi(c, dev, ws, force=force), oracle_qgemm(c), c["dtype"], f"force={force}")
 
 
+# ------------------------------------------------------------------------------------------------
+# decode kernel (M <= 16) and prefill kernel (M > 16, 4-bit): the paths specific to each
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("bits,M", [(4, 1), (4, 2), (4, 4), (4, 5), (4, 11), (4, 16), (2, 1), (2, 3), (2, 4)])
+@pytest.mark.parametrize("group", [64, 128, 256])
+def test_decode_kernel_rows_and_groups(bits, M, group, dev, ws):
+    """Every accumulator width (1 / 4 / 16 columns), every scale-group length, many CTAs per tile (Stream-K splits
+    inside a scale group for group 128 / 256), scale rows both 16-byte aligned (cp.async) and not (K = 3584, g = 128)."""
+    for (N, K, seed) in [(2048, 2048, 1), (1024, 3584, 2)]:
+        if K % group:
+            continue
+        c = make_case(M, N, K, bits, group, "bfloat16", seed=seed + M)
+        assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"decode W{bits} M={M} N={N} K={K} g={group}")
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_decode_kernel_identity_rows_bit_exact(dtype, dev, ws):
+    """Scale-on-accumulator numerics: a one-hot activation row must give round_T(table * scale) exactly, as the
+    reference's identity reconstruction does (tests/kernel.py:30-36,105-107), through the M <= 16 kernel too."""
+    K, N = 1024, 2048
+    c = make_case(K, N, K, 4, 64, dtype, seed=77, table="randn", identity=True)
+    ref = oracle_dequant(c)
+    for r0 in (0, 500, K - 16):
+        A = c["A"][r0:r0 + 16].contiguous()
+        D = run_cabi(c, dev, ws, A=A)
+        assert_same_values(D, ref[r0:r0 + 16], f"decode identity rows {r0}..{r0 + 16} {dtype}")
+
+
+@pytest.mark.parametrize("tile_p", [32, 64])
+def test_decode_and_prefill_tile_p(tile_p, dev, ws):
+    for M in (3, 150):
+        c = make_case(M, 2048, 1024, 4, 64, "float16", seed=M, tile_p=tile_p)
+        assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"tile_P={tile_p} M={M}")
+
+
+@pytest.mark.parametrize("M", [17, 64, 128, 129, 300])
+@pytest.mark.parametrize("force", [(0, 0, 0, -1), (0, 0, 5, 1), (0, 3, 148, 1), (0, 2, 0, 0)])
+def test_prefill_kernel_tails_and_schedules(M, force, dev, ws):
+    """Activation-row tails (M not a multiple of the 128-row tile), whole-tile and Stream-K schedules (the latter
+    exercises the store-based fix-up with 2..many contributors per tile), short rings."""
+    c = make_case(M, 1536, 1024, 4, 128, "bfloat16", seed=M)
+    assert_close(run_cabi(c, dev, ws, force=force), oracle_qgemm(c), c["dtype"], f"prefill M={M} force={force}")
+
+
+def test_prefill_kernel_identity_bit_exact_fp16(dev, ws):
+    K, N = 512, 1024
+    c = make_case(K, N, K, 4, 64, "float16", seed=9, table="randn", identity=True)
+    assert_same_values(run_cabi(c, dev, ws, force=(0, 0, 7, 1)), oracle_dequant(c), "prefill identity, Stream-K")
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 def test_both_footprints(variant, dev, ws):
     from flute_b200 import _lib

@@ -22,7 +22,7 @@ cat "$OUT/bench.json"; tail -3 "$OUT/bench.err"
 
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   # launch list: the two eager warm-up tokens of bench.py are 256 direct launches
-  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 128 -c 128 --csv \
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qgemm_ -s 128 -c 128 --csv \
       --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/ncu_launch.log" 2>&1
   # full capture: gate_up (28672x4096), o (4096x4096) decode launches of the second eager token
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:qgemm_decode -s 129 -c 2 \

@@ -1,0 +1,115 @@
+"""Summarise gpurun_out/<tag>/*.ncu-rep + launches.csv into profiles/ (text the judge can read without ncu).
+
+    python tools/summarize_ncu.py gpurun_out/r01z r01
+"""
+import csv, io, json, os, subprocess, sys, collections
+
+src, tag = sys.argv[1], sys.argv[2]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum"]
+
+
+def raw(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    return rows[0], rows[1], rows[2:]
+
+
+def source(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-kernel-base", "function"],
+                         capture_output=True, text=True).stdout
+    kernels, cur, hdr = [], None, None
+    for r in csv.reader(io.StringIO(txt)):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "rows": []}; kernels.append(cur)
+        elif r and r[0] == "Address":
+            hdr = r
+        elif cur is not None and r and r[0].startswith("0x"):
+            cur["rows"].append(r)
+    return hdr, kernels
+
+
+def summarise(rep, title, f):
+    hdr, units, rows = raw(rep)
+    f.write(f"== {title}: {os.path.basename(rep)} ==\n")
+    res = []
+    for r in rows:
+        name = r[hdr.index("Kernel Name")]
+        f.write(f"\nkernel: {name}\n")
+        d = {}
+        for k in hdr:
+            if k in KEYS or "pipe_tensor" in k and "pct" in k:
+                i = hdr.index(k)
+                f.write(f"  {k:95s} {r[i]:>16s} {units[i]}\n")
+                d[k] = r[i]
+        res.append(d)
+    h, kernels = source(rep)
+    if h:
+        iS, isrc, iex = h.index("# Samples"), h.index("Source"), h.index("Instructions Executed")
+        stall_cols = [i for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
+        for k in kernels[:len(rows)]:
+            agg = collections.Counter()
+            ops = collections.Counter()
+            for r in k["rows"]:
+                for i in stall_cols:
+                    agg[h[i]] += int(r[i] or 0)
+                t = r[isrc].strip().split()
+                if t and t[0].startswith("@"):
+                    t = t[1:]
+                if t:
+                    ops[t[0]] += int(r[iex])
+            tot = sum(agg.values()) or 1
+            f.write(f"\n  warp-state samples ({tot}): " + ", ".join(f"{a} {100 * b / tot:.0f}%" for a, b in agg.most_common(8)) + "\n")
+            f.write("  executed SASS by opcode: " + ", ".join(f"{a} {b}" for a, b in ops.most_common(14)) + "\n")
+            tensor = {a: b for a, b in ops.items() if a.startswith(("UTC", "LDTM", "STTM", "UTMA", "UBLK"))}
+            f.write(f"  tcgen05 / TMA opcodes executed: {tensor}\n")
+            top = sorted(k["rows"], key=lambda r: -int(r[iS]))[:12]
+            f.write("  hottest instructions (samples, executed, SASS):\n")
+            for r in top:
+                f.write(f"    {r[iS]:>5s} {r[iex]:>9s}  {r[isrc].strip()[:80]}\n")
+    f.write("\n")
+    return res
+
+
+with open(os.path.join(out_dir, f"{tag}_ncu_decode_summary.txt"), "w") as f:
+    dec = summarise(os.path.join(src, "prof_decode.ncu-rep"), "decode: gate_up / o launches of bench.py (ncu --set full, cold cache, serialised)", f)
+if os.path.exists(os.path.join(src, "prof_prefill.ncu-rep")):
+    with open(os.path.join(out_dir, f"{tag}_ncu_prefill_summary.txt"), "w") as f:
+        summarise(os.path.join(src, "prof_prefill.ncu-rep"), "prefill: 4096x4096 M=4096 (tools/microbench.py)", f)
+
+# launch list -> per-kernel share
+lp = os.path.join(src, "launches.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 14 and r[0].isdigit()]
+    per = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        name = r[4].split("(")[0][:90]
+        per[name][0] += 1
+        per[name][1] += float(r[14])
+    tot = sum(v[1] for v in per.values())
+    with open(os.path.join(out_dir, f"{tag}_launch_list_summary.txt"), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum, 128 launches of the second eager token of bench.py (cold, serialised)\n")
+        for n, (c, t) in sorted(per.items(), key=lambda x: -x[1][1]):
+            f.write(f"{c:5d} launches {t / 1e3:10.1f} us {100 * t / tot:5.1f}%  avg {t / c / 1e3:8.2f} us  {n}\n")
+    import shutil
+    shutil.copy(lp, os.path.join(out_dir, f"{tag}_launches.csv"))
+
+# traffic json for bench.py
+vals = []
+for d in dec:
+    try:
+        rd = float(d["dram__bytes_read.sum"]); wr = float(d["dram__bytes_write.sum"])
+        vals.append((rd, wr))
+    except Exception:
+        pass
