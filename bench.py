@@ -166,7 +166,36 @@ def build_model(torch, dev, tp, rank, seed=1234):
     return layers, table, table2
 
 
+class Progress:
+    """Phase log on stderr + a watchdog for multi-rank runs: a rank that makes no progress for `limit` seconds
+    prints what it was doing (rank 0: also a JSON line carrying the error) and exits instead of hanging the job."""
+
+    def __init__(self, rank, world, limit=180.0):
+        self.rank, self.world, self.limit = rank, world, limit
+        self.t0 = time.time()
+        self.last = self.t0
+        self.name = "start"
+        if world > 1:
+            threading.Thread(target=self._watch, daemon=True).start()
+
+    def __call__(self, name):
+        self.name, self.last = name, time.time()
+        print(f"[bench rank {self.rank} +{self.last - self.t0:6.1f}s] {name}", file=sys.stderr, flush=True)
+
+    def _watch(self):
+        while True:
+            time.sleep(5.0)
+            if time.time() - self.last > self.limit:
+                msg = f"rank {self.rank}: no progress for {self.limit:.0f} s in phase '{self.name}'"
+                print(f"[bench] WATCHDOG: {msg}", file=sys.stderr, flush=True)
+                if self.rank == 0:
+                    print(json.dumps({"metric": METRIC, "value": None, "unit": "tok/s", "n_gpus": self.world,
+                                      "error": msg}), flush=True)
+                os._exit(4)
+
+
 def run_own(args):
+    import datetime
     import torch
     import torch.distributed as dist
     import flute_b200
@@ -177,11 +206,22 @@ def run_own(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    progress = Progress(rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        progress("init_process_group(nccl)")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=150))
+        progress("first collective")
+        t = torch.ones(1, device=dev)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
     tp = world
+    # Collectives inside CUDA graphs: on for one GPU (none exist), opt-in for TP (FLUTE_B200_TP_GRAPH=1) until the
+    # captured-NCCL path has been validated on the target pool; the eager path launches 128 GEMMs + 128 all-gathers
+    # per token from the host.
+    use_graph = (world == 1) or os.environ.get("FLUTE_B200_TP_GRAPH", "0") == "1"
+    progress("build model")
 
     layers, table, table2 = build_model(torch, dev, tp, rank)
     ws = utils.get_workspace_streamk(dev)
@@ -225,33 +265,43 @@ def run_own(args):
         return x
 
     # ---- device-resident arm: one CUDA graph per step (128 PDL-chained launches) ----
+    progress("eager warm-up tokens")
     for _ in range(2):
-        token(x0, linear_cabi)
-    torch.cuda.synchronize()
-    side = torch.cuda.Stream()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
         launches[0] = 0
-        with torch.cuda.graph(graph, stream=side):
-            y = token(x0, linear_cabi)
+        token(x0, linear_cabi)
         launches_per_step = launches[0]
     torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    if use_graph:
+        progress("graph capture")
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            launches[0] = 0
+            with torch.cuda.graph(graph, stream=side):
+                y = token(x0, linear_cabi)
+            launches_per_step = launches[0]
+        torch.cuda.synchronize()
+        step = graph.replay
+    else:
+        step = lambda: token(x0, linear_cabi)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    progress("warm-up steps")
     for _ in range(max(3, args.warmup)):
-        graph.replay()
+        step()
     barrier()
+    progress("timed steps")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        graph.replay()
+        step()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -273,20 +323,31 @@ def run_own(args):
         x_dev.copy_(x_host, non_blocking=True)
         y_host.copy_(token(x_dev, linear_api), non_blocking=True)
     torch.cuda.synchronize()
-    graph2 = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph2, stream=side):
-            x_dev.copy_(x_host, non_blocking=True)
-            y2 = token(x_dev, linear_api)
-            y_host.copy_(y2, non_blocking=True)
-    torch.cuda.synchronize()
+
+    def e2e_eager():
+        x_dev.copy_(x_host, non_blocking=True)
+        y_host.copy_(token(x_dev, linear_api), non_blocking=True)
+
+    if use_graph:
+        progress("e2e graph capture")
+        graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph2, stream=side):
+                x_dev.copy_(x_host, non_blocking=True)
+                y2 = token(x_dev, linear_api)
+                y_host.copy_(y2, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_step = graph2.replay
+    else:
+        e2e_step = e2e_eager
+    progress("e2e steps")
     for _ in range(max(3, args.warmup)):
-        graph2.replay()
+        e2e_step()
         torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        graph2.replay()
+        e2e_step()
         torch.cuda.synchronize()          # the host consumes y_host every step
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -311,14 +372,17 @@ def run_own(args):
             "config": {"workload": "Llama-3-8B linears (qkv,o,gate_up,down x32) W4G64 bf16 decode M=1, linears only",
                        "parallelism": f"tp{tp}" if tp > 1 else "single", "packing": "tile_P=32",
                        "l2": "3.7 GB of distinct weights per step >> 126 MB L2 (no flush needed)",
-                       "launch": "one CUDA graph per step, 128 qgemm launches" + (", PDL-chained" if flags else "")},
+                       "launch": ("one CUDA graph per step, 128 qgemm launches" if use_graph else
+                                  "eager, 128 qgemm launches + 128 all-gathers per step from the host")
+                                 + (", PDL-chained" if flags else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": peak_kind, "traffic": traffic,
                          "algorithmic_bytes_per_launch_avg": nbytes / launches_per_step,
                          "kernel": "fb::dec::qgemm_decode_kernel<4,true,1>"},
             "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": x_host.numel() * 2,
                     "d2h_bytes_per_step": y_host.numel() * 2,
-                    "api": "flute_b200.qgemm_simple (torch op) x128 in one CUDA graph + pinned H2D/D2H, host sync per step"},
+                    "api": "flute_b200.qgemm_simple (torch op) x128 " + ("in one CUDA graph" if use_graph else "eager")
+                           + " + pinned H2D/D2H, host sync per step"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -332,8 +396,15 @@ def run_own(args):
                 "sample": f"o_proj 4096x4096 M=1 W4G64 bf16, best of 3 ({t_cpu:.2f} s; {w_cpu / 1e6:.1f}M of "
                           f"{total_weights() / 1e9:.2f}G weights/token, extrapolated)"}
         print(json.dumps(line), flush=True)
+    progress("done")
     if world > 1:
-        dist.destroy_process_group()
+        # tear the process group down, but never let a stuck teardown turn a finished measurement into a hang
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(20.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
