@@ -916,8 +916,13 @@ static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
 }  // namespace dec
 
 bool qgemm_decode_supported(const QgemmArgs& a) {
-    // 2-bit: eight accumulated fields per lane, so the register-resident accumulators stop at M = 4
-    return a.M >= 1 && ((a.num_bits == 4 && a.M <= 16) || (a.num_bits == 2 && a.M <= 4));
+    // Dispatched automatically for M <= 4.  For 5 <= M <= 16 (4-bit) the 16-accumulator variant works (tests pin it
+    // with flute_b200_set_variant(2)) but measured slower than the general kernel on B200 (gate_up M=16: 48 vs 40 us,
+    // profiles/r01_microbench_final.log vs r01_general_kernel_microbench_before.log), so it is opt-in for now.
+    // 2-bit: eight accumulated fields per lane, so the register-resident accumulators stop at M = 4.
+    if (a.M < 1) return false;
+    const int m_max = (a.num_bits == 4 && a.variant == 2) ? 16 : 4;
+    return (a.num_bits == 4 || a.num_bits == 2) && a.M <= m_max;
 }
 
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream) {

@@ -171,11 +171,16 @@ def test_schedules_agree(force, dev, ws):
 def test_decode_kernel_rows_and_groups(bits, M, group, dev, ws):
     """Every accumulator width (1 / 4 / 16 columns), every scale-group length, many CTAs per tile (Stream-K splits
     inside a scale group for group 128 / 256), scale rows both 16-byte aligned (cp.async) and not (K = 3584, g = 128)."""
-    for (N, K, seed) in [(2048, 2048, 1), (1024, 3584, 2)]:
-        if K % group:
-            continue
-        c = make_case(M, N, K, bits, group, "bfloat16", seed=seed + M)
-        assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"decode W{bits} M={M} N={N} K={K} g={group}")
+    from flute_b200 import _lib
+    _lib.lib.flute_b200_set_variant(2)      # the decode kernel also for 5 <= M <= 16 (opt-in: see qgemm_decode_supported)
+    try:
+        for (N, K, seed) in [(2048, 2048, 1), (1024, 3584, 2)]:
+            if K % group:
+                continue
+            c = make_case(M, N, K, bits, group, "bfloat16", seed=seed + M)
+            assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"decode W{bits} M={M} N={N} K={K} g={group}")
+    finally:
+        _lib.lib.flute_b200_set_variant(-1)
 
 
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
@@ -185,10 +190,16 @@ def test_decode_kernel_identity_rows_bit_exact(dtype, dev, ws):
     K, N = 1024, 2048
     c = make_case(K, N, K, 4, 64, dtype, seed=77, table="randn", identity=True)
     ref = oracle_dequant(c)
-    for r0 in (0, 500, K - 16):
-        A = c["A"][r0:r0 + 16].contiguous()
-        D = run_cabi(c, dev, ws, A=A)
-        assert_same_values(D, ref[r0:r0 + 16], f"decode identity rows {r0}..{r0 + 16} {dtype}")
+    from flute_b200 import _lib
+    for rows in (16, 4, 1):
+        _lib.lib.flute_b200_set_variant(2 if rows > 4 else -1)
+        try:
+            for r0 in (0, 500, K - rows):
+                A = c["A"][r0:r0 + rows].contiguous()
+                D = run_cabi(c, dev, ws, A=A)
+                assert_same_values(D, ref[r0:r0 + rows], f"decode identity rows {r0}..{r0 + rows} {dtype}")
+        finally:
+            _lib.lib.flute_b200_set_variant(-1)
 
 
 @pytest.mark.parametrize("tile_p", [32, 64])
