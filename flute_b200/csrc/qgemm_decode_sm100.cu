@@ -15,18 +15,24 @@
 //     product stays exact in fp32.  With A = I the result is round_T(T*S) -- bit-identical to the
 //     reference's reconstruction -- and for general A it differs by less than the reference's own
 //     tolerance (tests/kernel.py: 2e-3 fp16 / 1.1e-2 bf16).  See DESIGN.md "Decode numerics".
-//   * All 16 dequantiser warps work on the SAME 64-k stage (32 quarter-row pieces of 4 k-pairs each),
-//     so the latency of a stage is one piece, not one 128x32 chunk per warp, and a CTA that owns only
-//     three or four stages (4096x4096 over 148 SMs) still uses every warp.
-//   * Scales arrive by TMA ([tile columns] x [8 groups] blocks), no loader warps, no LDG latency on
-//     the critical path; accumulators live in registers, so there is no TMEM accumulator hand-off.
+//   * All 16 dequantiser warps convert quarter-row pieces (8 k-pairs per call) of the stages in flight -- two
+//     sets of 8 warps, one stage apart (4-bit) -- so the latency of a stage is one piece, not one 128x32 chunk
+//     per warp, and a CTA that owns only three or four stages (4096x4096 over 148 SMs) still uses every warp.
+//   * Scales ([tile columns] x [8 groups] blocks) and activation rows are copied with cp.async by their own
+//     warps; only the packed weights use TMA (a second TMA box per stage costs 18 % of the streaming rate,
+//     profiles/r01_probe_tma_stream.log).  Accumulators live in registers of the apply warps, so there is no
+//     TMEM accumulator hand-off; one tcgen05.commit per stage signals "smem stage free", "TMEM A slot free" and
+//     "group sums ready" at once.
 //
-// Warp roles (576 threads, 1 CTA/SM, persistent over a contiguous Stream-K range of (tile, k) stages):
-//   warps 0-15  dequantisers: warp w owns TMEM lane quarter w%4; within a stage it converts the
-//               k-pair quads {w/4, w/4 + 4} (4-bit) or {w/4} per half stage (2-bit).  The same warp
-//               applies the scales for field(s) w/4 and runs the epilogue for them.
-//   warp 16     TMA producer (packed weights + activations per stage, scale blocks per 8 groups)
-//   warp 17     tcgen05.mma issuer, TMEM allocator
+// Warp roles (1 CTA/SM, persistent over a contiguous Stream-K range of (tile, k) stages; 800 threads for
+// M <= 4, 896 for the opt-in 5 <= M <= 16 variant):
+//   warps 0-15   dequantisers: warp w owns TMEM lane quarter w%4 and the quads {4*((w/4)&1) .. +3} of its row in
+//                the stages of set w/8 (4-bit); {w/4} per half stage (2-bit)
+//   warp 16      TMA producer (packed weights, one 128-row x 64-k box per stage)
+//   warps 17,19  tcgen05.mma issuers (alternate scale groups; warp 17 also allocates TMEM)
+//   warp 18      activation rows of every stage (16-byte cp.async, three stages ahead)
+//   warps 20-23  (20-27) scale application (acc += S * P_g), epilogue and split-K fix-up, lane quarter = warp & 3
+//   warp 24      scale blocks (cp.async); for M > 4 the activation warp does this
 #include "ptx.cuh"
 #include "qgemm_sm100.h"
 
@@ -52,7 +58,6 @@ template <int BITS>
 struct DCfg;
 // NJ      pair fields per 32-bit word (accumulated output columns per packed row)
 // CK2     k-pairs per TMEM chunk (chunk = NJ*CK2 = 128 columns);  CPS chunks per 64-k stage
-// NFW     fields each dequant warp scales / stores (NJ / 4)
 template <>
 struct DCfg<4> {
     static constexpr int NJ = 4, CK2 = 32, CPS = 1, NFW = 1, LUTN = 256, A_SLOTS = 3, P_SLOTS = 2;
