@@ -1,0 +1,897 @@
+// EXPERIMENTAL half-SM variant of the decode kernel (4-bit, M <= 4): same algorithm and barrier protocol as
+// qgemm_decode_sm100.cu, resources cut in half so that TWO CTAs fit on an SM (512 threads, <= 64 registers,
+// 256 TMEM columns, ~105 KB shared memory: 32 KB LUT at stride 128, 3 ring stages, 2 scale slots).  Purpose:
+// with programmatic dependent launch the next kernel's CTAs become resident while this kernel still streams,
+// hiding the ~4.5 us of per-launch fixed cost that dominates the small Llama linears.
+// NOT dispatched by default and NOT yet validated on hardware: reachable only through
+// flute_b200_set_variant(3) (tests: FLUTE_B200_EXPERIMENTAL=1).
+//
+// Differences from the full-size kernel: 8 dequantiser warps (one set), half-stage TMEM chunks (64 columns, two
+// A slots) with a commit per chunk, LUT entries 128 bytes apart (PRMT + SHF instead of one PRMT per address),
+// the activation warp also copies the scale blocks, grid = 2 x SMs.
+#include "ptx.cuh"
+#include "qgemm_sm100.h"
+
+#include <cuda.h>
+
+namespace fb {
+namespace lite {
+
+// Optional per-role cycle accounting (profiling build only: python flute_b200/build.py --profile).
+#ifdef FB_PROFILE
+#define DPROF_DECL(...) long long __VA_ARGS__
+#define DPROF_T0(t) long long t = clock64()
+#define DPROF_ADD(acc, t) do { long long _n = clock64(); acc += _n - t; t = _n; } while (0)
+#define DPROF_OUT(slot, v) do { if (p.trace != nullptr) p.trace[blockIdx.x * 48 + (slot)] = (unsigned long long)(v); } while (0)
+#else
+#define DPROF_DECL(...)
+#define DPROF_T0(t)
+#define DPROF_ADD(acc, t)
+#define DPROF_OUT(slot, v)
+#endif
+
+template <int BITS>
+struct DCfg;
+// NJ      pair fields per 32-bit word (accumulated output columns per packed row)
+// CK2     k-pairs per TMEM chunk (chunk = NJ*CK2 = 128 columns);  CPS chunks per 64-k stage
+template <>
+struct DCfg<4> {
+    static constexpr int NJ = 4, CK2 = 16, CPS = 2, NFW = 1, LUTN = 256, A_SLOTS = 2, P_SLOTS = 2;
+};
+template <>
+struct DCfg<2> {
+    static constexpr int NJ = 8, CK2 = 16, CPS = 2, NFW = 2, LUTN = 16, A_SLOTS = 2, P_SLOTS = 2;
+};
+
+constexpr int kDqWarps = 8;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+constexpr int kActWarp = 10;          // activation rows (cp.async) 
+constexpr int kMmaWarpB = 11;          // second MMA issuer: flush groups alternate between the two
+constexpr int kApplyWarp0 = 12;       // scale/accumulate/epilogue warps, lane quarter = warp & 3
+// apply warps: 4 (each all NJ fields) for M <= 4; 8 (two field halves) when a field needs 16 accumulators
+__host__ __device__ constexpr int apply_warps(int) { return 4; }
+// M <= 4: one more warp copies the scale blocks; M > 4 (8 apply warps, register budget): the activation warp does
+__host__ __device__ constexpr bool has_scale_warp(int) { return false; }   // the activation warp copies the scale blocks
+__host__ __device__ constexpr int threads_for(int mc) { return (kApplyWarp0 + apply_warps(mc) + (has_scale_warp(mc) ? 1 : 0)) * 32; }
+constexpr int kMaxStages = 4;
+constexpr int kScSlots = 2;
+constexpr int kLutStride = 128;      // bytes between LUT entries: ((code << 8) | lane*8) >> 1
+constexpr int kWBytes = 128 * 128;   // packed-weight part of a stage: 128 rows x 64 k x 2 B
+constexpr int kBBytes = 16 * 128;    // activation part: 16 rows x 64 k x 2 B
+constexpr int kStageBytes = kWBytes + kBBytes;
+constexpr int kMb = 16;              // MMA N
+
+struct Ctl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t a_full[3];
+    uint64_t a_empty[3];
+    uint64_t p_full[2];
+    uint64_t p_empty[2];
+    uint64_t sc_full[kScSlots];
+    uint64_t sc_empty[kScSlots];
+    uint32_t tmem_base;
+    int is_last;
+};
+
+struct DecodeParams {
+    const uint16_t* A;
+    const uint16_t* S;
+    const uint32_t* table2;
+    uint16_t* D;
+    uint8_t* workspace;
+    Diag* diag;
+    unsigned long long* trace;
+    int M, N, K, G;
+    int tile_p;
+    int gshift;          // log2(group_size / 64): stages per group
+    int n_tiles, k_iters;
+    int stages;
+    int tma_scales;      // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
+    int static_weights;
+    int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
+    uint32_t partial_offset;
+};
+
+enum : int { DSITE_FULL = 21, DSITE_AEMPTY, DSITE_PFULL, DSITE_SCFULL, DSITE_EMPTY, DSITE_SCEMPTY, DSITE_AFULL, DSITE_PEMPTY };
+
+static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t bar, uint32_t parity, int iter) {
+    if (diag != nullptr) {
+        diag->block = blockIdx.x;
+        diag->warp = threadIdx.x >> 5;
+        diag->site = site;
+        diag->index = (int)bar;
+        diag->parity = (int)parity;
+        diag->iter = iter;
+        diag->code = 1;
+        __threadfence_system();
+    }
+    __trap();
+}
+
+// Lean bounded wait: one try_wait on the fast path; the bound is a spin count (each failed try_wait
+// already suspends the warp for a hardware-defined interval), checked out of line.
+__device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const DecodeParams& p, int site, int iter = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // 4 s: trap, don't hang
+        }
+    }
+}
+
+// One elected lane of a converged warp.  tcgen05.mma / commit / TMA are uniform-datapath instructions: under
+// `if (lane == 0)` ptxas cannot prove uniformity and wraps each one in an ELECT ... BRA.U.ANY waterfall loop
+// (~210 cycles per MMA measured, tools/mma_rate_probe.cu); under elect.sync it issues them directly.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+// (byte J of w) << 8 | lane4  -- the LUT offset of pair-code byte J for this lane
+template <int J>
+__device__ __forceinline__ uint32_t code_lane(uint32_t w, uint32_t lane4) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(lane4), "n"(0x6504 + (J << 4)));   // lane4 holds lane*8 here
+    return r >> 1;
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t (&r)[1]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+template <int MC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[MC]) {
+    if constexpr (MC == 1) tmem_ld_x1(taddr, r);
+    else if constexpr (MC == 4) tmem_ld_x4(taddr, r);
+    else tmem_ld_32x32b_x16(taddr, r);
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void tma_load_3d_nohint(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_nohint(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+template <int BITS, int NJ>
+__device__ __forceinline__ int n_local(int L, int j, int tile_p) {
+    if (tile_p == 32) return (L >> 5) * (NJ * 32) + j * 32 + (L & 31);
+    return (L >> 6) * (NJ * 64) + j * 64 + (L & 63);
+}
+
+struct Range {
+    int it0, it1;
+};
+__device__ __forceinline__ Range cta_range(int total, int b, int grid) {
+    const int base = total / grid, rem = total - base * grid;
+    Range r;
+    r.it0 = b * base + min(b, rem);
+    r.it1 = r.it0 + base + (b < rem ? 1 : 0);
+    return r;
+}
+__device__ __forceinline__ int cta_of(int total, int it, int grid) {
+    const int base = total / grid, rem = total - base * grid;
+    const int thr = rem * (base + 1);
+    return it < thr ? it / (base + 1) : rem + (it - thr) / base;
+}
+
+// One piece: 4 consecutive k-pairs of row L -> NJ x (4 TMEM columns).
+template <int BITS>
+struct Piece;
+template <>
+struct Piece<4> {
+    // two 16-byte quads (8 consecutive k-pairs) of row L -> 4 fields x 8 TMEM columns
+    static __device__ __forceinline__ void run(uint32_t row, int pq0, int pq1, uint32_t lut, uint32_t lane4, uint32_t tcol) {
+        const uint4 v0 = lds128(row + (uint32_t)(pq0 << 4));
+        const uint4 v1 = lds128(row + (uint32_t)(pq1 << 4));
+        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t r[4][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            r[0][i] = lds32(lut + code_lane<0>(w[i], lane4));
+            r[1][i] = lds32(lut + code_lane<1>(w[i], lane4));
+            r[2][i] = lds32(lut + code_lane<2>(w[i], lane4));
+            r[3][i] = lds32(lut + code_lane<3>(w[i], lane4));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * 16, r[j]);
+    }
+};
+template <>
+struct Piece<2> {
+    static __device__ __forceinline__ void run(uint32_t row, int pq, uint32_t lut, uint32_t lane4, uint32_t tcol) {
+        const uint4 v = lds128(row + (uint32_t)(pq << 4));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t r[8][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t lo = w[i] & 0x0f0f0f0fu;          // nibbles 0, 2, 4, 6 as bytes
+            const uint32_t hi = (w[i] >> 4) & 0x0f0f0f0fu;   // nibbles 1, 3, 5, 7
+            r[0][i] = lds32(lut + code_lane<0>(lo, lane4));
+            r[1][i] = lds32(lut + code_lane<0>(hi, lane4));
+            r[2][i] = lds32(lut + code_lane<1>(lo, lane4));
+            r[3][i] = lds32(lut + code_lane<1>(hi, lane4));
+            r[4][i] = lds32(lut + code_lane<2>(lo, lane4));
+            r[5][i] = lds32(lut + code_lane<2>(hi, lane4));
+            r[6][i] = lds32(lut + code_lane<3>(lo, lane4));
+            r[7][i] = lds32(lut + code_lane<3>(hi, lane4));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tmem_st_x4(tcol + j * 16, r[j][0], r[j][1], r[j][2], r[j][3]);
+    }
+};
+
+template <bool BF16>
+__device__ __forceinline__ float scale_to_f32(uint32_t s16) {
+    if constexpr (BF16) return __uint_as_float(s16 << 16);
+    else return __half2float(__ushort_as_half((unsigned short)s16));
+}
+
+template <int BITS, bool BF16, int MC>
+__global__ void __launch_bounds__(threads_for(MC), 2)
+qgemm_decode_lite_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodeParams p) {
+    using F = DCfg<BITS>;
+    constexpr int NJ = F::NJ, CK2 = F::CK2, CPS = F::CPS;
+    constexpr int AS = F::A_SLOTS, PS = F::P_SLOTS;
+    constexpr int TN = NJ * 128;
+    constexpr uint32_t kScBytes = TN * 16;
+    constexpr uint32_t kACols = NJ * CK2;          // TMEM columns of one A slot (a 32-k half stage)
+    constexpr uint32_t kPCol0 = AS * kACols;       // P slots sit after the A slots
+    constexpr uint32_t kPCols = NJ * kMb;
+    constexpr int kApplyWarps = apply_warps(MC);
+    constexpr int kScaleWarp = kApplyWarp0 + kApplyWarps;   // exists iff has_scale_warp(MC)
+    constexpr int NFA = NJ / (kApplyWarps / 4);   // fields per apply warp
+    static_assert(kPCol0 + PS * kPCols <= 256, "TMEM budget");
+    static_assert(BITS == 4 && MC <= 4, "lite variant: 4-bit, M <= 4");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t ring = smem_base;
+    const uint32_t sc_smem = ring + p.stages * kStageBytes;
+    const uint32_t lut = sc_smem + kScSlots * kScBytes;
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem_gen + (lut + F::LUTN * kLutStride - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int grid = gridDim.x;
+    const int total = p.n_tiles * p.k_iters;
+    const Range rg = cta_range(total, blockIdx.x, grid);
+    const int spg_mask = (1 << p.gshift) - 1;
+
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 0] = globaltimer_ns();
+    if (!p.static_weights) pdl_wait_prior_grids();
+
+    if (warp == kProducerWarp && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&ctl->full[s]), 2);   // TMA (expect_tx) + the activation rows
+            mbar_init(smem_u32(&ctl->empty[s]), 1);
+        }
+        for (int s = 0; s < AS; ++s) {
+            mbar_init(smem_u32(&ctl->a_full[s]), kDqWarps);
+            mbar_init(smem_u32(&ctl->a_empty[s]), 1);
+        }
+        for (int s = 0; s < PS; ++s) {
+            mbar_init(smem_u32(&ctl->p_full[s]), 1);
+            mbar_init(smem_u32(&ctl->p_empty[s]), kApplyWarps);
+        }
+        for (int s = 0; s < kScSlots; ++s) {
+            mbar_init(smem_u32(&ctl->sc_full[s]), 32);   // one (deferred) arrival per lane of the activation/scale warp
+            mbar_init(smem_u32(&ctl->sc_empty[s]), kApplyWarps);
+        }
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem_alloc(smem_u32(&ctl->tmem_base), 256);
+        tmem_relinquish();
+    }
+    // First sync: barriers + TMEM address visible; the producer starts streaming right after it while the
+    // dequant warps are still building the LUT (second, dequant-only sync below).
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ctl->tmem_base;
+    pdl_launch_dependents();
+
+    // One step of the scale-block schedule (called once per stage, in stage order, by ONE warp): when stage (tile, k)
+    // starts a new block of 8 groups, copy [tile columns] x [8 groups] (16 bytes per row) into the next scale slot.
+    // cp.async, not TMA: as a TMA box the 512 sixteen-byte rows cost the producer ~2000 cycles of issue time per
+    // block (measured), during which no weight tile could be requested.
+    auto scale_step = [&](int tile, int k, int& nb, int& last_blk) {
+        const int blk = (k >> p.gshift) >> 3;
+        if (blk == last_blk) return;
+        const int slot = nb % kScSlots;
+        const uint32_t par = ((nb / kScSlots) & 1) ^ 1u;
+        wait(smem_u32(&ctl->sc_empty[slot]), par, p, DSITE_SCEMPTY);
+        const uint32_t dst = sc_smem + slot * kScBytes;
+        if (p.tma_scales) {
+#pragma unroll 4
+            for (int r = lane; r < TN; r += 32) {
+                const int n = tile * TN + r;
+                if (n < p.N) {
+                    const uint16_t* src = p.S + (size_t)n * p.G + blk * 8;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 16), "l"(src) : "memory");
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&ctl->sc_full[slot])) : "memory");
+        } else {
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(smem_gen + (dst - smem_base));
+            for (int r = lane; r < TN; r += 32) {
+                const int n = tile * TN + r;
+#pragma unroll
+                for (int gi = 0; gi < 8; ++gi) {
+                    const int g = blk * 8 + gi;
+                    d16[r * 8 + gi] = (n < p.N && g < p.G) ? __ldg(p.S + (size_t)n * p.G + g) : (uint16_t)0;
+                }
+            }
+            mbar_arrive(smem_u32(&ctl->sc_full[slot]));
+        }
+        last_blk = blk;
+        ++nb;
+    };
+
+    if (warp == kProducerWarp) {
+        // =============================== TMA producer ===============================
+        // Packed weights by TMA, one 128-row x 64-k box per stage.  Static data: nothing here waits for the previous kernel.
+        if (rg.it1 > rg.it0) {
+            const uint64_t pol_w = policy_evict_first();
+            const int n_it = rg.it1 - rg.it0;
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
+            int stage = 0;
+            uint32_t ephase = 1;           // parity to wait on `empty` (first pass: free)
+            DPROF_DECL(pw_sc = 0, pw_empty = 0, pw_w = 0, pw_a = 0);
+            DPROF_T0(pt);
+            for (int i = 0; i < n_it; ++i) {
+                DPROF_ADD(pw_sc, pt);
+                wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
+                DPROF_ADD(pw_empty, pt);
+                if (elect_one()) {
+                    const uint32_t bar = smem_u32(&ctl->full[stage]);
+                    mbar_arrive_expect_tx(bar, kWBytes);
+                    tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, tile * 128, pol_w);
+                }
+                __syncwarp();
+                DPROF_ADD(pw_w, pt);
+                DPROF_ADD(pw_a, pt);
+                if (++stage == p.stages) { stage = 0; ephase ^= 1u; }
+                if (++k == p.k_iters) { k = 0; ++tile; }
+            }
+            if (lane == 0) { DPROF_OUT(8, pw_sc); DPROF_OUT(9, pw_empty); DPROF_OUT(10, pw_w); DPROF_OUT(11, pw_a); DPROF_OUT(12, n_it); }
+        }
+    } else if (warp == kMmaWarp || warp == kMmaWarpB) {
+        // =============================== MMA issuers ================================
+        // Two issuing warps take alternate flush groups (all stages of one scale group go to the same warp, so
+        // the first MMA of a group overwrites and the rest accumulate in issue order).  Group f uses P slot
+        // f & 1, i.e. each warp owns one P slot.  A single issuer spends as long waiting on barriers and
+        // committing as the tensor pipe spends on the 16 N=16 MMAs of a stage (~16 cycles each, measured:
+        // tools/mma_rate_probe.cu), which made it the slowest role of the pipeline.
+        if (rg.it1 > rg.it0) {
+            const int mine = (warp == kMmaWarp) ? 0 : 1;
+            const uint32_t idesc = make_idesc_f16(BF16, 128, kMb);
+            int stage = 0;
+            int aslot = 0;
+            uint32_t aphase = 0;
+            int f = 0;                     // flush groups started so far
+            bool grp_first = true;
+            DPROF_DECL(mw_afull = 0, mw_pempty = 0, mw_issue = 0);
+            DPROF_T0(mt);
+            for (int it = rg.it0; it < rg.it1;) {
+                const int tile = it / p.k_iters;
+                const int kb = it - tile * p.k_iters;
+                const int ke = min(p.k_iters, kb + (rg.it1 - it));
+                for (int k = kb; k < ke; ++k) {
+                    const bool my_group = ((f & 1) == mine);
+                    if (my_group) {
+                        // (no wait on full[stage]: every dequant warp observed it before arriving on a_full)
+                        const uint64_t bdesc = make_smem_desc_sw128(ring + stage * kStageBytes + kWBytes);
+                        const int pslot = mine;
+#pragma unroll
+                        for (int c = 0; c < CPS; ++c) {
+                            wait(smem_u32(&ctl->a_full[aslot]), aphase, p, DSITE_AFULL);
+                            DPROF_ADD(mw_afull, mt);
+                            if (grp_first) wait(smem_u32(&ctl->p_empty[pslot]), (((uint32_t)f >> 1) & 1u) ^ 1u, p, DSITE_PEMPTY);
+                            DPROF_ADD(mw_pempty, mt);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t a_base = tmem + aslot * kACols;
+                                const uint32_t d_base = tmem + kPCol0 + pslot * kPCols;
+                                if (!(p.ablate & 1))
+#pragma unroll
+                                for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+                                    for (int kk = 0; kk < CK2 / 8; ++kk) {
+                                        tc_mma_ts(d_base + j * kMb, a_base + j * CK2 + kk * 8,
+                                                  bdesc + (uint64_t)(((c * CK2 + kk * 8) * 4) >> 4), idesc,
+                                                  (grp_first && kk == 0) ? 0u : 1u);
+                                    }
+                                }
+                                // one completion signal per stage: frees the smem stage (producer, activation warp), the
+                                // TMEM A slot (dequantisers, AS/CPS stages later) and publishes the group sums (apply warps)
+                                if (c == CPS - 1) tc_commit(smem_u32(&ctl->empty[stage]));
+                                else tc_commit(smem_u32(&ctl->a_empty[aslot]));
+                            }
+                            __syncwarp();
+                            grp_first = false;
+                            if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                        }
+                        DPROF_ADD(mw_issue, mt);
+                    } else {
+                        // Not mine, but stay in step with every a_full phase: a parity wait is only meaningful for
+                        // the NEXT completion of a barrier, so this warp must not run a whole phase ahead of it.
+#pragma unroll
+                        for (int c = 0; c < CPS; ++c) {
+                            wait(smem_u32(&ctl->a_full[aslot]), aphase, p, DSITE_AFULL);
+                            if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                        }
+                    }
+                    const bool flush = (((k + 1) & spg_mask) == 0) || (k == ke - 1);
+                    if (flush) { grp_first = true; ++f; }
+                    if (++stage == p.stages) stage = 0;
+                }
+                it += ke - kb;
+            }
+            if (lane == 0 && mine == 0) { DPROF_OUT(14, mw_afull); DPROF_OUT(15, mw_pempty); DPROF_OUT(16, mw_issue); }
+        }
+    } else if (warp == kActWarp) {
+        // =============================== activation rows ============================
+        // The activation tile of a stage (M rows x 64 k inside a 16-row, 128-byte-swizzled K-major tile) is written
+        // with 16-byte cp.async copies, three stages ahead, instead of a second TMA box: measured on B200
+        // (tools/tma_stream_probe.cu) every cp.async.bulk.tensor costs the TMA unit ~160 cycles + ~2.7 per
+        // 128-byte row, and a second box per 64-k stage (even with one in-bounds row) costs 18 % of the streaming
+        // rate.  Rows >= M of every stage's tile are zeroed once and never written again.
+        if (rg.it1 > rg.it0) {
+            constexpr int D = 3;
+            const int n_it = rg.it1 - rg.it0;
+            for (int s2 = 0; s2 < p.stages; ++s2) {
+                uint4* z = reinterpret_cast<uint4*>(smem_gen + (ring + s2 * kStageBytes + kWBytes - smem_base));
+#pragma unroll
+                for (int i = 0; i < kBBytes / 16 / 32; ++i) z[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
+            int stage = 0, astage = 0;
+            uint32_t ephase = 1;
+            int nb = 0;                    // scale blocks issued
+            int last_blk = -1;
+            const int r0 = lane >> 3, c16 = lane & 7;          // this lane's row (mod 4) and 16-byte chunk
+            const uint8_t* a_lane = reinterpret_cast<const uint8_t*>(p.A) + c16 * 16;
+            for (int i = 0; i < n_it; ++i) {
+                if (!has_scale_warp(MC)) scale_step(tile, k, nb, last_blk);
+                wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
+                const uint32_t bt = ring + stage * kStageBytes + kWBytes;
+#pragma unroll
+                for (int m0 = 0; m0 < MC; m0 += 4) {
+                    const int r = m0 + r0;
+                    if (r < p.M) {
+                        const uint32_t dst = bt + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+                        const uint8_t* src = a_lane + ((size_t)r * p.K + (size_t)k * 64) * 2;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (i >= D) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(D) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[astage]));
+                    if (++astage == p.stages) astage = 0;
+                }
+                if (++stage == p.stages) { stage = 0; ephase ^= 1u; }
+                if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            for (int i = max(0, n_it - D); i < n_it; ++i) {
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->full[astage]));
+                if (++astage == p.stages) astage = 0;
+            }
+        }
+    } else if (has_scale_warp(MC) && warp == kScaleWarp) {
+        // =============================== scale blocks ===============================
+        if (rg.it1 > rg.it0) {
+            const int n_it = rg.it1 - rg.it0;
+            int tile = rg.it0 / p.k_iters;
+            int k = rg.it0 - tile * p.k_iters;
+            int nb = 0, last_blk = -1;
+            for (int i = 0; i < n_it; ++i) {
+                scale_step(tile, k, nb, last_blk);
+                if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
+            }
+        }
+    } else if (warp >= kApplyWarp0) {
+        // ===================== scale + accumulate + epilogue ========================
+        const int q = warp & 3;
+        const int L = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const int fset = (warp - kApplyWarp0) >> 2;        // which NFA-field subset this warp owns
+        int nloc[NFA];
+#pragma unroll
+        for (int j = 0; j < NFA; ++j) nloc[j] = n_local<BITS, NJ>(L, fset * NFA + j, p.tile_p);
+        const bool do_apply = !(p.ablate & 4);
+        int pslot = 0;
+        int stage = 0;                     // ring slot / phase of the stage the loop is at
+        uint32_t dphase = 0;
+        int sc_idx = 0;
+        uint32_t sc_par = 0;
+        bool synced = false;
+        DPROF_DECL(aw_pfull = 0, aw_sc = 0, aw_work = 0, aw_epi = 0);
+        DPROF_T0(at);
+        for (int it = rg.it0; it < rg.it1;) {
+            const int tile = it / p.k_iters;
+            const int kb = it - tile * p.k_iters;
+            const int ke = min(p.k_iters, kb + (rg.it1 - it));
+            float acc[NFA][MC];
+#pragma unroll
+            for (int j = 0; j < NFA; ++j)
+#pragma unroll
+                for (int m = 0; m < MC; ++m) acc[j][m] = 0.f;
+            int cur_blk = -1;
+            auto release_scales = [&]() {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->sc_empty[sc_idx]));
+                if (++sc_idx == kScSlots) { sc_idx = 0; sc_par ^= 1u; }
+            };
+            for (int k = kb; k < ke; ++k) {
+                const bool flush = (((k + 1) & spg_mask) == 0) || (k == ke - 1);
+                const int fstage = stage;
+                const uint32_t fpar = dphase;
+                if (++stage == p.stages) { stage = 0; dphase ^= 1u; }
+                if (!flush) continue;
+                const int g = k >> p.gshift;
+                const int blk = g >> 3;
+                if (blk != cur_blk) {
+                    if (cur_blk >= 0) release_scales();
+                    cur_blk = blk;
+                    wait(smem_u32(&ctl->sc_full[sc_idx]), sc_par, p, DSITE_SCFULL);
+                }
+                DPROF_ADD(aw_sc, at);
+                const uint32_t sc_base = sc_smem + sc_idx * kScBytes + (g & 7) * 2;
+                float sc[NFA];
+#pragma unroll
+                for (int j = 0; j < NFA; ++j) sc[j] = scale_to_f32<BF16>(lds16(sc_base + nloc[j] * 16));
+                wait(smem_u32(&ctl->empty[fstage]), fpar, p, DSITE_PFULL);   // every MMA of the group has completed
+                DPROF_ADD(aw_pfull, at);
+                tc_fence_after();
+                const uint32_t pcol = tmem + lane_sel + kPCol0 + pslot * kPCols;
+                if (do_apply) {
+                    if constexpr (MC <= 4) {
+                        uint32_t r[NFA][MC];
+#pragma unroll
+                        for (int j = 0; j < NFA; ++j) tmem_ld_cols<MC>(pcol + (fset * NFA + j) * kMb, r[j]);
+                        tc_wait_ld();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctl->p_empty[pslot]));
+#pragma unroll
+                        for (int j = 0; j < NFA; ++j)
+#pragma unroll
+                            for (int m = 0; m < MC; ++m) acc[j][m] = fmaf(sc[j], __uint_as_float(r[j][m]), acc[j][m]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NFA; ++j) {
+                            uint32_t r[MC];
+                            tmem_ld_cols<MC>(pcol + (fset * NFA + j) * kMb, r);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int m = 0; m < MC; ++m) acc[j][m] = fmaf(sc[j], __uint_as_float(r[m]), acc[j][m]);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&ctl->p_empty[pslot]));
+                    }
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->p_empty[pslot]));
+                }
+                if (++pslot == PS) pslot = 0;
+                DPROF_ADD(aw_work, at);
+            }
+            if (cur_blk >= 0) release_scales();
+
+            // ------------------------------- epilogue ------------------------------------
+            if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 4] = globaltimer_ns();
+            if (!synced) { pdl_wait_prior_grids(); synced = true; }
+            const bool full_k = (kb == 0) && (ke == p.k_iters);
+            const int n_base = tile * TN;
+            if (full_k) {
+#pragma unroll
+                for (int j = 0; j < NFA; ++j) {
+                    const int n = n_base + nloc[j];
+                    if (n < p.N) {
+#pragma unroll
+                        for (int m = 0; m < MC; ++m)
+                            if (m < p.M) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(acc[j][m]);
+                    }
+                }
+            } else {
+                // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left
+                // zero on exit); the CTA that arrives last converts and writes the tile.
+                const int tile_it0 = tile * p.k_iters;
+                const int first_cta = cta_of(total, tile_it0, grid);
+                const int contributors = cta_of(total, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
+                float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
+#pragma unroll
+                for (int j = 0; j < NFA; ++j)
+#pragma unroll
+                    for (int m = 0; m < MC; ++m)
+                        if (m < p.M) red_add_f32(accum + ((fset * NFA + j) * kMb + m) * 128 + L, acc[j][m]);
+                asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
+                if (warp == kApplyWarp0 && lane == 0) {
+                    const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
+                    const int last = (old == contributors - 1) ? 1 : 0;
+                    if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
+                    ctl->is_last = last;
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
+                if (ctl->is_last) {
+#pragma unroll
+                    for (int j = 0; j < NFA; ++j) {
+                        const int n = n_base + nloc[j];
+#pragma unroll
+                        for (int m = 0; m < MC; ++m) {
+                            if (m < p.M) {
+                                float* src = accum + ((fset * NFA + j) * kMb + m) * 128 + L;
+                                const float v = __ldcg(src);
+                                *src = 0.f;
+                                if (n < p.N) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(v);
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");   // is_last is reused by the next segment
+            }
+            if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 5] = globaltimer_ns();
+            DPROF_ADD(aw_epi, at);
+            it += ke - kb;
+        }
+        if (lane == 0 && warp == kApplyWarp0) { DPROF_OUT(40, aw_sc); DPROF_OUT(41, aw_pfull); DPROF_OUT(42, aw_work); DPROF_OUT(43, aw_epi); }
+    } else {
+        // ========================= dequantisers + scale + epilogue =====================
+        const int q = warp & 3;                 // TMEM lane quarter
+        const int sw = warp >> 2;               // 0..3: piece column set, and the field(s) this warp scales
+        const int L = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const uint32_t lane4 = (uint32_t)lane * 8;     // see code_lane: (code << 8 | lane*8) >> 1 = code*128 + lane*4
+        {   // lane-replicated LUT: entry e for lane l at lut + e*256 + l*4
+            uint32_t* lut_gen = reinterpret_cast<uint32_t*>(smem_gen + (lut - smem_base));
+            const int t = threadIdx.x;      // 0..255
+            {
+                const uint32_t v = __ldg(p.table2 + (t & 255));        // 256 dequant threads, one entry each
+#pragma unroll
+                for (int l = 0; l < 32; ++l) lut_gen[(t & 255) * (kLutStride / 4) + l] = v;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
+        }
+        if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 1] = globaltimer_ns();
+
+        const uint32_t wrow = (uint32_t)L * 128;
+        const int xq = L & 7;
+        const bool do_dq = !(p.ablate & 2);
+        // DQG stage groups: with DQG == 2 the 16 warps split into two sets of 8 that convert alternate stages
+        // (each warp: 4 quads = 16 k-pairs of its row).  During the conversion of a stage the shared-memory
+        // crossbar is the limiter (16 B of packed words + 32 x 4 B of LUT reads per lane = 640 wavefronts per
+        // stage); with every warp on the SAME stage the barrier waits of all warps coincide and the crossbar
+        // idles ~1/3 of the time.  Two sets, one stage apart, fill each other's gaps.
+        constexpr int DQG = 1;
+        const int grp = (DQG == 2) ? (sw >> 1) : 0;
+        const int hw = (DQG == 2) ? (sw & 1) : sw;          // position inside the set
+        DPROF_DECL(dw_full = 0, dw_aempty = 0, dw_piece = 0, dw_st = 0);
+        DPROF_T0(dt);
+        const int n_it = rg.it1 - rg.it0;
+        const int S = p.stages;
+        // ring slot / parity of stage i, and of stage t = i - AS/CPS whose completion frees this stage's last A slot
+        int stage = grp % S;
+        uint32_t fphase = (uint32_t)(grp / S) & 1u;
+        int tstage = 0;
+        uint32_t tphase = 0;
+        {
+            const int t0 = grp - AS / CPS + ((grp < AS / CPS) ? DQG * ((AS / CPS - grp + DQG - 1) / DQG) : 0);   // first t >= 0
+            tstage = t0 % S;
+            tphase = (uint32_t)(t0 / S) & 1u;
+        }
+        int chunk = grp * CPS;             // global chunk index of (stage i, c = 0)
+        int aslot = chunk % AS;
+        uint32_t aphase = ((uint32_t)(chunk / AS) & 1u) ^ 1u;
+        for (int i = grp; i < n_it; i += DQG) {
+            wait(smem_u32(&ctl->full[stage]), fphase, p, DSITE_FULL);
+            DPROF_ADD(dw_full, dt);
+            const uint32_t row = ring + stage * kStageBytes + wrow;
+#pragma unroll
+            for (int c = 0; c < CPS; ++c) {
+                if (c == CPS - 1) {
+                    if (i >= AS / CPS) {
+                        wait(smem_u32(&ctl->empty[tstage]), tphase, p, DSITE_AEMPTY);
+                        tstage += DQG;
+                        if (tstage >= S) { tstage -= S; tphase ^= 1u; }
+                    }
+                } else {
+                    wait(smem_u32(&ctl->a_empty[aslot]), aphase, p, DSITE_AEMPTY, i * 1000 + n_it);
+                }
+                DPROF_ADD(dw_aempty, dt);
+                tc_fence_after();
+                const uint32_t tcol = tmem + lane_sel + aslot * kACols;
+                if (do_dq) {
+                    // half stage c: this warp's 8 k-pairs are the 16-byte quads 4*c + 2*hw and 4*c + 2*hw + 1 of row L
+                    Piece<4>::run(row, (4 * c + 2 * hw) ^ xq, (4 * c + 2 * hw + 1) ^ xq, lut, lane4, tcol + hw * 8);
+                }
+                DPROF_ADD(dw_piece, dt);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
+                if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                DPROF_ADD(dw_st, dt);
+            }
+            // skip the chunks of the stages the other set converts
+#pragma unroll
+            for (int x = 0; x < (DQG - 1) * CPS; ++x)
+                if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+            stage += DQG;
+            if (stage >= S) { stage -= S; fphase ^= 1u; }
+        }
+#ifdef FB_PROFILE
+        if (lane == 0 && (warp == 0 || warp == 5)) {
+            const int o = (warp == 0) ? 24 : 32;
+            DPROF_OUT(o + 0, dw_full); DPROF_OUT(o + 1, dw_aempty); DPROF_OUT(o + 2, dw_piece); DPROF_OUT(o + 3, dw_st);
+        }
+#endif
+    }
+
+    // ---- teardown ------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 7] = globaltimer_ns();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+template <int BITS, bool BF16, int MC>
+static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
+    using F = DCfg<BITS>;
+    constexpr int TN = F::NJ * 128;
+    DecodeParams p{};
+    p.A = static_cast<const uint16_t*>(a.A);
+    p.S = static_cast<const uint16_t*>(a.S);
+    p.table2 = static_cast<const uint32_t*>(a.table2);
+    p.D = static_cast<uint16_t*>(a.D);
+    p.workspace = static_cast<uint8_t*>(a.workspace);
+    p.diag = a.diag;
+    p.trace = a.trace;
+    p.M = a.M; p.N = a.N; p.K = a.K;
+    p.G = a.K / a.group_size;
+    p.tile_p = a.tile_p;
+    p.gshift = (a.group_size == 64) ? 0 : (a.group_size == 128) ? 1 : 2;
+    p.n_tiles = (a.N + TN - 1) / TN;
+    p.k_iters = a.K / 64;
+    p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
+    p.ablate = a.ablate;
+    p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
+
+    const uint32_t fixed = kScSlots * TN * 16 + F::LUTN * kLutStride + sizeof(Ctl) + 1024 /*alignment slack*/;
+    const uint32_t smem_budget = 115712u;      // (228 KB - 2 x 1 KB reserved) / 2: two CTAs per SM
+    int stages = (int)((smem_budget - fixed) / kStageBytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
+    if (stages < 2) return FB_ERR_INTERNAL;
+    p.stages = stages;
+    const uint32_t smem_bytes = stages * kStageBytes + fixed;
+
+    const long long total = (long long)p.n_tiles * p.k_iters;
+    if (total > 0x3fffffffLL) return FB_ERR_SHAPE;
+    int grid = 2 * a.num_sms;
+    if (a.force_grid > 0) grid = a.force_grid;
+    if (grid > total) grid = (int)total;
+
+    constexpr size_t kCounterBytes = 65536;
+    p.partial_offset = (uint32_t)kCounterBytes;
+    const size_t need = kCounterBytes + (size_t)p.n_tiles * F::NJ * kMb * 128 * 4;
+    if ((size_t)p.n_tiles * 4 > kCounterBytes || need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
+
+    CUtensorMap tm_w;
+    const uint64_t P = (uint64_t)a.N / 16 * BITS;
+    int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, 64, 128,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FB_OK) return rc;
+    auto kern = qgemm_decode_lite_kernel<BITS, BF16, MC>;
+    static bool attr_set[64] = {};
+    if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
+            cudaGetLastError();
+            return FB_ERR_LAUNCH;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set[a.device] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads_for(MC));
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    int nattr = 0;
+    if (a.flags & FB_FLAG_PDL) {
+        attrs[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = nattr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_LAUNCH;
+    }
+    return FB_OK;
+}
+
+template <int BITS, bool BF16>
+static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
+    if (a.M == 1) return launch_t<BITS, BF16, 1>(a, stream);
+    if (a.M <= 4) return launch_t<BITS, BF16, 4>(a, stream);
+    return FB_ERR_INTERNAL;
+}
+
+}  // namespace lite
+
+bool qgemm_decode_lite_supported(const QgemmArgs& a) { return a.num_bits == 4 && a.M >= 1 && a.M <= 4; }
+
+int qgemm_decode_lite_launch(const QgemmArgs& a, cudaStream_t stream) {
+    return a.bf16 ? lite::launch_mc<4, true>(a, stream) : lite::launch_mc<4, false>(a, stream);
+}
+
+}  // namespace fb

@@ -69,6 +69,9 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);
 // decode-shaped kernel (M <= 16, 2/4-bit): qgemm_decode_sm100.cu
 bool qgemm_decode_supported(const QgemmArgs& a);
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream);
+// experimental half-SM decode kernel (4-bit, M <= 4; variant 3 only): qgemm_decode_lite_sm100.cu
+bool qgemm_decode_lite_supported(const QgemmArgs& a);
+int qgemm_decode_lite_launch(const QgemmArgs& a, cudaStream_t stream);
 // prefill-shaped kernel (M > 16, 4-bit): qgemm_prefill_sm100.cu
 // The tail of the workspace holds its per-CTA partial-tile slots (2 x 128 KB per SM, contents undefined between
 // launches); the zero-invariant fp32 accumulators of the other kernels must stay below it.

@@ -6,6 +6,7 @@ GEMM must reproduce the dequantised weight bit for bit (tests/kernel.py:30-36,10
 agree with `torch.mm(A, W_hat)` evaluated on the GPU in T (the reference tests' own ground truth,
 tests/kernel.py:68-71) within 2.0e-3 (fp16) / 1.0e-2 (bf16)."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -222,6 +223,20 @@ def test_prefill_kernel_identity_bit_exact_fp16(dev, ws):
     K, N = 512, 1024
     c = make_case(K, N, K, 4, 64, "float16", seed=9, table="randn", identity=True)
     assert_same_values(run_cabi(c, dev, ws, force=(0, 0, 7, 1)), oracle_dequant(c), "prefill identity, Stream-K")
+
+
+@pytest.mark.skipif(os.environ.get("FLUTE_B200_EXPERIMENTAL") != "1",
+                    reason="half-SM decode kernel (qgemm_decode_lite_sm100.cu): opt-in until validated on hardware")
+@pytest.mark.parametrize("M", [1, 3, 4])
+def test_experimental_decode_lite(M, dev, ws):
+    from flute_b200 import _lib
+    _lib.lib.flute_b200_set_variant(3)
+    try:
+        for (N, K, group, seed) in [(1024, 512, 64, 1), (2048, 2048, 128, 2), (4096, 4096, 64, 3), (1024, 3584, 128, 4)]:
+            c = make_case(M, N, K, 4, group, "bfloat16", seed=seed + M)
+            assert_close(run_cabi(c, dev, ws), oracle_qgemm(c), c["dtype"], f"lite M={M} N={N} K={K} g={group}")
+    finally:
+        _lib.lib.flute_b200_set_variant(-1)
 
 
 @pytest.mark.parametrize("variant", [0, 1])
