@@ -378,6 +378,8 @@ def run_own(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_kind": peak_kind, "traffic": traffic,
                          "algorithmic_bytes_per_launch_avg": nbytes / launches_per_step,
+                         "basis": "algorithmic bytes of a step / device time of the step (CUDA events); the step is 128 "
+                                  "back-to-back launches of this one kernel, so inter-launch gaps count against it",
                          "kernel": "fb::dec::qgemm_decode_kernel<4,true,1>"},
             "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": x_host.numel() * 2,
                     "d2h_bytes_per_step": y_host.numel() * 2,
