@@ -52,6 +52,27 @@ def _call_qgemm(M=1, N=512, K=256, bits=4, group=64, tile_p=32, dtype=0, ptr=0x1
     (dict(bits=3, N=1024 + 256), -4),                             # 3-bit needs N % 512 == 0            utils.py:146-155
     (dict(tile_p=16), -5), (dict(bits=3, tile_p=64, N=1024), -5),  # utils.py:138-139
 ])
+def test_workspace_layout_fits_every_baseline_shape():
+    """[64 KB counters | zero-invariant fp32 accumulators | ... | 2 x 128 KB per SM of prefill
+    partial-tile slots].  The reference-sized workspace must hold the largest accumulator region any BASELINE.json
+    shape needs below the scratch tail (mirrors the checks in csrc/qgemm_*_sm100.cu)."""
+    from flute_b200 import _lib
+    sms = 148
+    total = _lib.lib.flute_b200_workspace_bytes(sms)
+    scratch = sms * 2 * 131072 + 256
+    counters = 65536
+    shapes = [(6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (10240, 8192), (8192, 8192), (57344, 8192),
+              (8192, 28672), (28672, 3584)]
+    for (N, K) in shapes:
+        # decode kernel, 4-bit: one [4 fields][16][128] fp32 block per 512-column tile
+        need = counters + ((N + 511) // 512) * 4 * 16 * 128 * 4
+        assert need + scratch <= total, (N, K)
+        # general kernel, Stream-K at M = 64 (4 fields x 64 rows x 128 lanes fp32 per tile, one activation-row tile)
+        need = counters + ((N + 511) // 512) * 4 * 64 * 128 * 4
+        assert need + scratch <= total, (N, K)
+        assert ((N + 511) // 512) * 2 * ((4096 + 127) // 128) * 4 <= counters        # prefill tile counters at M = 4096
+
+
 def test_cabi_validation_errors(kwargs, code):
     """Argument validation happens before any device is touched, so it is testable without a GPU."""
     rc = _call_qgemm(**kwargs)
