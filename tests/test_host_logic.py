@@ -44,14 +44,6 @@ def _call_qgemm(M=1, N=512, K=256, bits=4, group=64, tile_p=32, dtype=0, ptr=0x1
     return _lib.lib.flute_b200_qgemm(p, p, p, p, p, p, p, 1 << 20, M, N, K, bits, group, tile_p, dtype, 0, 0, None)
 
 
-@pytest.mark.parametrize("kwargs,code", [
-    (dict(bits=5), -1), (dict(bits=1), -1),                       # AT_ERROR("Unsupported `num_bits`")  qgemm.cpp:171
-    (dict(group=32), -2), (dict(group=96), -2),                   # AT_ERROR("Unsupported `group_size`") qgemm.cpp:153
-    (dict(dtype=2), -3),                                          # dtype dispatch                       qgemm.cpp:176-193
-    (dict(K=100), -4), (dict(K=320, group=128), -4), (dict(N=500), -4), (dict(M=-1), -4),
-    (dict(bits=3, N=1024 + 256), -4),                             # 3-bit needs N % 512 == 0            utils.py:146-155
-    (dict(tile_p=16), -5), (dict(bits=3, tile_p=64, N=1024), -5),  # utils.py:138-139
-])
 def test_workspace_layout_fits_every_baseline_shape():
     """[64 KB counters | zero-invariant fp32 accumulators | ... | 2 x 128 KB per SM of prefill
     partial-tile slots].  The reference-sized workspace must hold the largest accumulator region any BASELINE.json
@@ -73,6 +65,14 @@ def test_workspace_layout_fits_every_baseline_shape():
         assert ((N + 511) // 512) * 2 * ((4096 + 127) // 128) * 4 <= counters        # prefill tile counters at M = 4096
 
 
+@pytest.mark.parametrize("kwargs,code", [
+    (dict(bits=5), -1), (dict(bits=1), -1),                       # AT_ERROR("Unsupported `num_bits`")  qgemm.cpp:171
+    (dict(group=32), -2), (dict(group=96), -2),                   # AT_ERROR("Unsupported `group_size`") qgemm.cpp:153
+    (dict(dtype=2), -3),                                          # dtype dispatch                       qgemm.cpp:176-193
+    (dict(K=100), -4), (dict(K=320, group=128), -4), (dict(N=500), -4), (dict(M=-1), -4),
+    (dict(bits=3, N=1024 + 256), -4),                             # 3-bit needs N % 512 == 0            utils.py:146-155
+    (dict(tile_p=16), -5), (dict(bits=3, tile_p=64, N=1024), -5),  # utils.py:138-139
+])
 def test_cabi_validation_errors(kwargs, code):
     """Argument validation happens before any device is touched, so it is testable without a GPU."""
     rc = _call_qgemm(**kwargs)
