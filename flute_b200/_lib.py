@@ -81,6 +81,8 @@ def _load() -> ctypes.CDLL:
 
 
 lib = _load()
+if os.environ.get("FLUTE_B200_VARIANT"):          # tools / A-B runs only: pin a kernel variant for the whole process
+    lib.flute_b200_set_variant(int(os.environ["FLUTE_B200_VARIANT"], 0))
 
 
 def check(rc: int) -> None:

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflute_b200.so")
-SOURCES = ["qgemm_sm100.cu", "qgemm_decode_sm100.cu", "qgemm_decode_lite_sm100.cu", "qgemm_prefill_sm100.cu", "aux_kernels.cu", "api.cu"]
+SOURCES = ["qgemm_sm100.cu", "qgemm_decode_sm100.cu", "qgemm_prefill_sm100.cu", "aux_kernels.cu", "api.cu"]
 HEADERS = ["ptx.cuh", "qgemm_sm100.h", "aux_kernels.h", os.path.join("..", "..", "include", "flute_b200.h")]
 
 NVCC_FLAGS = [

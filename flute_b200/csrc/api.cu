@@ -35,6 +35,7 @@ DeviceState g_dev[kMaxDevices];
 long g_timeout_ms = 10000;
 unsigned long long* g_trace = nullptr;
 int g_ablate = 0;
+int g_l2_prefetch = -1;                   // test hook: decode kernel's L2 prefetch distance (-1 = engine's choice)
 int g_variant = -1;                       // test hook: kernel footprint override   // test hook: per-CTA globaltimer stamps
 
 struct DeviceGuard {
@@ -134,6 +135,7 @@ int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* 
     a.trace = g_trace;
     a.variant = g_variant;
     a.ablate = g_ablate;
+    a.l2_prefetch = g_l2_prefetch;
     a.timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
     a.force_mb = force_mb; a.force_stages = force_stages; a.force_grid = force_grid; a.force_streamk = force_streamk;
     rc = fb::qgemm_launch(a, static_cast<cudaStream_t>(stream));
@@ -275,10 +277,11 @@ int flute_b200_version(void) { return FLUTE_B200_VERSION; }
 void flute_b200_set_timeout_ms(long ms) { g_timeout_ms = ms; }
 
 void flute_b200_set_variant(int variant) {
-    if (variant < 0) { g_variant = -1; g_ablate = 0; return; }
+    if (variant < 0) { g_variant = -1; g_ablate = 0; g_l2_prefetch = -1; return; }
     g_variant = variant & 0xff;
     if (g_variant == 0xff) g_variant = -1;
     g_ablate = (variant >> 8) & 0xff;   // undocumented perf-ablation bits, tools/microbench.py only
+    g_l2_prefetch = ((variant >> 16) & 0xff) - 1;   // tools only: 0 = engine's choice, n + 1 = prefetch n stages
 }
 
 void flute_b200_set_trace_buffer(void* device_ptr) { g_trace = static_cast<unsigned long long*>(device_ptr); }

@@ -15,24 +15,33 @@
 //     product stays exact in fp32.  With A = I the result is round_T(T*S) -- bit-identical to the
 //     reference's reconstruction -- and for general A it differs by less than the reference's own
 //     tolerance (tests/kernel.py: 2e-3 fp16 / 1.1e-2 bf16).  See DESIGN.md "Decode numerics".
-//   * All 16 dequantiser warps convert quarter-row pieces (8 k-pairs per call) of the stages in flight -- two
-//     sets of 8 warps, one stage apart (4-bit) -- so the latency of a stage is one piece, not one 128x32 chunk
-//     per warp, and a CTA that owns only three or four stages (4096x4096 over 148 SMs) still uses every warp.
+//   * All dequantiser warps convert quarter-row pieces (8 k-pairs per call) of the stages in flight, so the
+//     latency of a stage is one piece, not one 128x32 chunk per warp, and a CTA that owns only three or four
+//     stages (4096x4096 over 148 SMs) still uses every warp.
 //   * Scales ([tile columns] x [8 groups] blocks) and activation rows are copied with cp.async by their own
 //     warps; only the packed weights use TMA (a second TMA box per stage costs 18 % of the streaming rate,
 //     profiles/r01_probe_tma_stream.log).  Accumulators live in registers of the apply warps, so there is no
 //     TMEM accumulator hand-off; one tcgen05.commit per stage signals "smem stage free", "TMEM A slot free" and
 //     "group sums ready" at once.
 //
-// Warp roles (1 CTA/SM, persistent over a contiguous Stream-K range of (tile, k) stages; 800 threads for
-// M <= 4, 896 for the opt-in 5 <= M <= 16 variant):
-//   warps 0-15   dequantisers: warp w owns TMEM lane quarter w%4 and the quads {4*((w/4)&1) .. +3} of its row in
-//                the stages of set w/8 (4-bit); {w/4} per half stage (2-bit)
-//   warp 16      TMA producer (packed weights, one 128-row x 64-k box per stage)
-//   warps 17,19  tcgen05.mma issuers (alternate scale groups; warp 17 also allocates TMEM)
-//   warp 18      activation rows of every stage (16-byte cp.async, three stages ahead)
-//   warps 20-23  (20-27) scale application (acc += S * P_g), epilogue and split-K fix-up, lane quarter = warp & 3
-//   warp 24      scale blocks (cp.async); for M > 4 the activation warp does this
+// Two footprints of the SAME kernel (template parameter HALF; not a fork):
+//   HALF = false  one CTA per SM: 16 dequantiser warps (two sets, one stage apart), 214 KB shared memory,
+//                 512 TMEM columns.
+//   HALF = true   (4-bit, M <= 4) half an SM: 8 dequantiser warps, 512 threads / <= 64 registers, <= 113 KB of
+//                 shared memory (32 KB LUT in a folded layout, 3 ring stages), 256 TMEM columns, grid = #SMs.
+//                 Two such CTAs fit on an SM, so with programmatic dependent launch the NEXT qgemm's CTAs are
+//                 resident while this one still streams: their set-up (barriers, TMEM, LUT), the tensor-map
+//                 fetch, their first weight tiles (static weights) and an L2 prefetch of the tiles after those run
+//                 under this kernel's stream instead of costing ~7 us per launch.
+//
+// Warp roles (persistent over a contiguous Stream-K range of (tile, k) stages).  DQ = dequantiser warps
+// (16, HALF: 8); 800 threads for M <= 4, 896 for the opt-in 5 <= M <= 16 variant, 512 for HALF:
+//   warps 0..DQ-1    dequantisers: warp w owns TMEM lane quarter w%4 and a fixed set of 16-byte quads of its row
+//   warp DQ          TMA producer (packed weights, one 128-row x 64-k box per stage; optional L2 prefetch ahead)
+//   warps DQ+1,DQ+3  tcgen05.mma issuers (alternate scale groups; warp DQ+1 also allocates TMEM)
+//   warp DQ+2        activation rows of every stage (16-byte cp.async, up to three stages ahead)
+//   warps DQ+4..     4 (8 for M > 4) scale application (acc += S * P_g), epilogue and split-K fix-up
+//   last warp        scale blocks (cp.async); for M > 4 and for HALF the activation warp does this
 #include "ptx.cuh"
 #include "qgemm_sm100.h"
 
@@ -54,47 +63,54 @@ namespace dec {
 #define DPROF_OUT(slot, v)
 #endif
 
-template <int BITS>
-struct DCfg;
 // NJ      pair fields per 32-bit word (accumulated output columns per packed row)
-// CK2     k-pairs per TMEM chunk (chunk = NJ*CK2 = 128 columns);  CPS chunks per 64-k stage
+// CK2     k-pairs per TMEM chunk (an A slot = NJ*CK2 columns);  CPS chunks per 64-k stage
+// DQ      dequantiser warps;  DQG sets of them that convert alternate stages
+// LUTB    bytes of the lane-replicated pair LUT
+template <int BITS, bool HALF>
+struct DCfg;
 template <>
-struct DCfg<4> {
-    static constexpr int NJ = 4, CK2 = 32, CPS = 1, NFW = 1, LUTN = 256, A_SLOTS = 3, P_SLOTS = 2;
+struct DCfg<4, false> {
+    static constexpr int NJ = 4, CK2 = 32, CPS = 1, LUTN = 256, A_SLOTS = 3, P_SLOTS = 2;
+    static constexpr int DQ = 16, DQG = 2, SC_SLOTS = 3, MAX_STAGES = 10, TMEM_COLS = 512, LUTB = 256 * 256;
+    static constexpr uint32_t SMEM_BUDGET = 232448u;
 };
 template <>
-struct DCfg<2> {
-    static constexpr int NJ = 8, CK2 = 16, CPS = 2, NFW = 2, LUTN = 16, A_SLOTS = 2, P_SLOTS = 2;
+struct DCfg<4, true> {
+    static constexpr int NJ = 4, CK2 = 16, CPS = 2, LUTN = 256, A_SLOTS = 2, P_SLOTS = 2;
+    static constexpr int DQ = 8, DQG = 1, SC_SLOTS = 2, MAX_STAGES = 4, TMEM_COLS = 256, LUTB = 256 * 128;
+    static constexpr uint32_t SMEM_BUDGET = 115712u;      // (228 KB - 2 x 1 KB reserved) / 2: two CTAs per SM
+};
+template <>
+struct DCfg<2, false> {
+    static constexpr int NJ = 8, CK2 = 16, CPS = 2, LUTN = 16, A_SLOTS = 2, P_SLOTS = 2;
+    static constexpr int DQ = 16, DQG = 1, SC_SLOTS = 3, MAX_STAGES = 10, TMEM_COLS = 512, LUTB = 16 * 256;
+    static constexpr uint32_t SMEM_BUDGET = 232448u;
 };
 
-constexpr int kDqWarps = 16;
-constexpr int kProducerWarp = 16;
-constexpr int kMmaWarp = 17;
-constexpr int kActWarp = 18;          // activation rows (cp.async) 
-constexpr int kMmaWarpB = 19;          // second MMA issuer: flush groups alternate between the two
-constexpr int kApplyWarp0 = 20;       // scale/accumulate/epilogue warps, lane quarter = warp & 3
 // apply warps: 4 (each all NJ fields) for M <= 4; 8 (two field halves) when a field needs 16 accumulators
 __host__ __device__ constexpr int apply_warps(int mc) { return mc > 4 ? 8 : 4; }
-// M <= 4: one more warp copies the scale blocks; M > 4 (8 apply warps, register budget): the activation warp does
-__host__ __device__ constexpr bool has_scale_warp(int mc) { return mc <= 4; }
-__host__ __device__ constexpr int threads_for(int mc) { return (kApplyWarp0 + apply_warps(mc) + (has_scale_warp(mc) ? 1 : 0)) * 32; }
-constexpr int kMaxStages = 10;
-constexpr int kScSlots = 3;
-constexpr int kLutStride = 256;      // bytes between LUT entries: (code << 8) | lane*4 is ONE prmt
+// full footprint, M <= 4: one more warp copies the scale blocks; otherwise the activation warp does
+__host__ __device__ constexpr bool has_scale_warp(int mc, bool half) { return mc <= 4 && !half; }
+__host__ __device__ constexpr int threads_for(int dq, int mc, bool half) {
+    return (dq + 4 + apply_warps(mc) + (has_scale_warp(mc, half) ? 1 : 0)) * 32;
+}
+constexpr int kMaxStagesAny = 10;
+constexpr int kMaxScSlots = 3;
 constexpr int kWBytes = 128 * 128;   // packed-weight part of a stage: 128 rows x 64 k x 2 B
 constexpr int kBBytes = 16 * 128;    // activation part: 16 rows x 64 k x 2 B
 constexpr int kStageBytes = kWBytes + kBBytes;
 constexpr int kMb = 16;              // MMA N
 
 struct Ctl {
-    uint64_t full[kMaxStages];
-    uint64_t empty[kMaxStages];
+    uint64_t full[kMaxStagesAny];
+    uint64_t empty[kMaxStagesAny];
     uint64_t a_full[3];
     uint64_t a_empty[3];
     uint64_t p_full[2];
     uint64_t p_empty[2];
-    uint64_t sc_full[kScSlots];
-    uint64_t sc_empty[kScSlots];
+    uint64_t sc_full[kMaxScSlots];
+    uint64_t sc_empty[kMaxScSlots];
     uint32_t tmem_base;
     int is_last;
 };
@@ -107,6 +123,7 @@ struct DecodeParams {
     uint8_t* workspace;
     Diag* diag;
     unsigned long long* trace;
+    unsigned long long timeout_ns;   // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
     int M, N, K, G;
     int tile_p;
     int gshift;          // log2(group_size / 64): stages per group
@@ -115,6 +132,7 @@ struct DecodeParams {
     int tma_scales;      // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
     int static_weights;
     int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
+    int l2_prefetch;     // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
     uint32_t partial_offset;
 };
 
@@ -134,17 +152,17 @@ static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t 
     __trap();
 }
 
-// Lean bounded wait: one try_wait on the fast path; the bound is a spin count (each failed try_wait
-// already suspends the warp for a hardware-defined interval), checked out of line.
+// Lean bounded wait: one try_wait on the fast path; the bound (p.timeout_ns, 0 = none) is checked out of line
+// every 1024 failed probes (each failed try_wait already suspends the warp for a hardware-defined interval).
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const DecodeParams& p, int site, int iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0) {
+        if ((++spins & 0x3ff) == 0 && p.timeout_ns != 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // 4 s: trap, don't hang
+            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
         }
     }
 }
@@ -173,12 +191,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-// (byte J of w) << 8 | lane4  -- the LUT offset of pair-code byte J for this lane
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// (byte J of w) << 8 | lane4  -- the LUT offset of pair-code byte J for this lane (256-byte entry stride)
 template <int J>
 __device__ __forceinline__ uint32_t code_lane(uint32_t w, uint32_t lane4) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(lane4), "n"(0x6504 + (J << 4)));
     return r;
+}
+// Folded 32 KB LUT (HALF): entry e of lane l sits at (e & 127) * 256 + (e >> 7) * 128 + l * 4, so the offset is
+// still ONE prmt per code -- byte 1 = code & 0x7f (from w7 = w & 0x7f7f7f7f), byte 0 = (code & 0x80) | lane*4 (from
+// x = (w & 0x80808080) | lane4 replicated), bytes 2..3 = sign-replicated byte of w7 = 0 -- plus two LOP3 per WORD of
+// four codes (2.5 instead of 2 issue slots per pair; a shift of the 256-stride offset would cost 3).
+template <int J>
+__device__ __forceinline__ uint32_t code_lane_folded(uint32_t w7, uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w7), "r"(x), "n"(((8 | J) << 12) | ((8 | J) << 8) | (J << 4) | (4 + J)));
+    return r;
+}
+__host__ __device__ constexpr uint32_t lut_entry_offset(int e, bool folded) {
+    return folded ? (uint32_t)((e & 127) * 256 + (e >> 7) * 128) : (uint32_t)(e * 256);
 }
 __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
@@ -210,17 +244,10 @@ __device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
     return old;
 }
-__device__ __forceinline__ void tma_load_3d_nohint(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_nohint(uint32_t dst_smem, const void* tmap, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
+// Pull one packed-weight box into L2 without a shared-memory destination.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1) : "memory");
 }
 
 template <int BITS, int NJ>
@@ -245,12 +272,13 @@ __device__ __forceinline__ int cta_of(int total, int it, int grid) {
     return it < thr ? it / (base + 1) : rem + (it - thr) / base;
 }
 
-// One piece: 4 consecutive k-pairs of row L -> NJ x (4 TMEM columns).
+// One piece of a dequantiser warp's work on row L of a stage.
 template <int BITS>
 struct Piece;
 template <>
 struct Piece<4> {
-    // two 16-byte quads (8 consecutive k-pairs) of row L -> 4 fields x 8 TMEM columns
+    // two 16-byte quads (8 consecutive k-pairs) of row L -> 4 fields x 8 TMEM columns, field blocks FSTRIDE columns apart
+    template <bool FOLDED, int FSTRIDE>
     static __device__ __forceinline__ void run(uint32_t row, int pq0, int pq1, uint32_t lut, uint32_t lane4, uint32_t tcol) {
         const uint4 v0 = lds128(row + (uint32_t)(pq0 << 4));
         const uint4 v1 = lds128(row + (uint32_t)(pq1 << 4));
@@ -258,13 +286,23 @@ struct Piece<4> {
         uint32_t r[4][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            r[0][i] = lds32(lut + code_lane<0>(w[i], lane4));
-            r[1][i] = lds32(lut + code_lane<1>(w[i], lane4));
-            r[2][i] = lds32(lut + code_lane<2>(w[i], lane4));
-            r[3][i] = lds32(lut + code_lane<3>(w[i], lane4));
+            if constexpr (FOLDED) {
+                const uint32_t w7 = w[i] & 0x7f7f7f7fu;
+                uint32_t x;      // (w & 0x80808080) | lane4 (lane*4 replicated into every byte)
+                asm("lop3.b32 %0, %1, 0x80808080, %2, 0xEA;" : "=r"(x) : "r"(w[i]), "r"(lane4));
+                r[0][i] = lds32(lut + code_lane_folded<0>(w7, x));
+                r[1][i] = lds32(lut + code_lane_folded<1>(w7, x));
+                r[2][i] = lds32(lut + code_lane_folded<2>(w7, x));
+                r[3][i] = lds32(lut + code_lane_folded<3>(w7, x));
+            } else {
+                r[0][i] = lds32(lut + code_lane<0>(w[i], lane4));
+                r[1][i] = lds32(lut + code_lane<1>(w[i], lane4));
+                r[2][i] = lds32(lut + code_lane<2>(w[i], lane4));
+                r[3][i] = lds32(lut + code_lane<3>(w[i], lane4));
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * 32, r[j]);
+        for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * FSTRIDE, r[j]);
     }
 };
 template <>
@@ -297,20 +335,31 @@ __device__ __forceinline__ float scale_to_f32(uint32_t s16) {
     else return __half2float(__ushort_as_half((unsigned short)s16));
 }
 
-template <int BITS, bool BF16, int MC>
-__global__ void __launch_bounds__(threads_for(MC), 1)
+template <int BITS, bool BF16, int MC, bool HALF>
+__global__ void __launch_bounds__(threads_for(DCfg<BITS, HALF>::DQ, MC, HALF), HALF ? 2 : 1)
 qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodeParams p) {
-    using F = DCfg<BITS>;
+    using F = DCfg<BITS, HALF>;
     constexpr int NJ = F::NJ, CK2 = F::CK2, CPS = F::CPS;
     constexpr int AS = F::A_SLOTS, PS = F::P_SLOTS;
+    constexpr int kDqWarps = F::DQ;
+    constexpr int kProducerWarp = kDqWarps;
+    constexpr int kMmaWarp = kDqWarps + 1;
+    constexpr int kActWarp = kDqWarps + 2;          // activation rows (cp.async)
+    constexpr int kMmaWarpB = kDqWarps + 3;         // second MMA issuer: flush groups alternate between the two
+    constexpr int kApplyWarp0 = kDqWarps + 4;       // scale/accumulate/epilogue warps, lane quarter = warp & 3
+    constexpr int kScSlots = F::SC_SLOTS;
     constexpr int TN = NJ * 128;
     constexpr uint32_t kScBytes = TN * 16;
-    constexpr uint32_t kPCol0 = AS * 128;          // P slots sit after the A slots
+    constexpr uint32_t kACols = NJ * CK2;          // TMEM columns of one A slot
+    constexpr uint32_t kPCol0 = AS * kACols;       // P slots sit after the A slots
     constexpr uint32_t kPCols = NJ * kMb;
     constexpr int kApplyWarps = apply_warps(MC);
-    constexpr int kScaleWarp = kApplyWarp0 + kApplyWarps;   // exists iff has_scale_warp(MC)
+    constexpr bool kScaleWarpExists = has_scale_warp(MC, HALF);
+    constexpr int kScaleWarp = kApplyWarp0 + kApplyWarps;   // exists iff kScaleWarpExists
     constexpr int NFA = NJ / (kApplyWarps / 4);   // fields per apply warp
-    static_assert(kPCol0 + PS * kPCols <= 512, "TMEM budget");
+    static_assert(kPCol0 + PS * kPCols <= (uint32_t)F::TMEM_COLS, "TMEM budget");
+    static_assert(!HALF || (BITS == 4 && MC <= 4), "half-SM footprint: 4-bit, M <= 4");
+    static_assert((kApplyWarp0 & 3) == 0, "apply warp w must own TMEM lane quarter w & 3");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -318,7 +367,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     const uint32_t ring = smem_base;
     const uint32_t sc_smem = ring + p.stages * kStageBytes;
     const uint32_t lut = sc_smem + kScSlots * kScBytes;
-    Ctl* ctl = reinterpret_cast<Ctl*>(smem_gen + (lut + F::LUTN * kLutStride - smem_base));
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem_gen + (lut + F::LUTB - smem_base));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -337,7 +386,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
         for (int s = 0; s < AS; ++s) {
-            mbar_init(smem_u32(&ctl->a_full[s]), (BITS == 4) ? kDqWarps / 2 : kDqWarps);
+            mbar_init(smem_u32(&ctl->a_full[s]), kDqWarps / F::DQG);
             mbar_init(smem_u32(&ctl->a_empty[s]), 1);
         }
         for (int s = 0; s < PS; ++s) {
@@ -351,7 +400,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         mbar_fence_init();
     }
     if (warp == kMmaWarp) {
-        tmem_alloc(smem_u32(&ctl->tmem_base), 512);
+        tmem_alloc(smem_u32(&ctl->tmem_base), F::TMEM_COLS);
         tmem_relinquish();
     }
     // First sync: barriers + TMEM address visible; the producer starts streaming right after it while the
@@ -401,7 +450,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 
     if (warp == kProducerWarp) {
         // =============================== TMA producer ===============================
-        // Packed weights by TMA, one 128-row x 64-k box per stage.  Static data: nothing here waits for the previous kernel.
+        // Packed weights by TMA, one 128-row x 64-k box per stage.  Static data: nothing here waits for the previous
+        // kernel.  With l2_prefetch = PF > 0 the boxes of the next PF stages beyond the ring are pulled into L2 first
+        // (no shared-memory destination), so that a short ring (HALF: 3 stages) still keeps enough bytes in flight
+        // towards HBM, and a CTA that is resident early (PDL) warms L2 with its first 3 + PF stages while it waits.
         if (rg.it1 > rg.it0) {
             const uint64_t pol_w = policy_evict_first();
             const int n_it = rg.it1 - rg.it0;
@@ -409,6 +461,14 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             int k = rg.it0 - tile * p.k_iters;
             int stage = 0;
             uint32_t ephase = 1;           // parity to wait on `empty` (first pass: free)
+            // L2 prefetch cursor: stage index pf_i with coordinates (pf_tile, pf_k); runs p.stages + PF ahead of i
+            const int pf_ahead = p.l2_prefetch > 0 ? p.stages + p.l2_prefetch : 0;
+            int pf_i = min(n_it, p.stages);
+            int pf_tile = tile, pf_k = k;
+            if (pf_ahead > 0) {
+                pf_k += pf_i;
+                while (pf_k >= p.k_iters) { pf_k -= p.k_iters; ++pf_tile; }
+            }
             DPROF_DECL(pw_sc = 0, pw_empty = 0, pw_w = 0, pw_a = 0);
             DPROF_T0(pt);
             for (int i = 0; i < n_it; ++i) {
@@ -419,6 +479,12 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     const uint32_t bar = smem_u32(&ctl->full[stage]);
                     mbar_arrive_expect_tx(bar, kWBytes);
                     tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, tile * 128, pol_w);
+                    const int pf_end = min(n_it, i + 1 + pf_ahead);
+                    while (pf_i < pf_end) {       // first iterations: catch up; steady state: one box per stage
+                        tma_prefetch_l2_2d(&tmap_w, pf_k * 64, pf_tile * 128);
+                        ++pf_i;
+                        if (++pf_k == p.k_iters) { pf_k = 0; ++pf_tile; }
+                    }
                 }
                 __syncwarp();
                 DPROF_ADD(pw_w, pt);
@@ -462,8 +528,9 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                             if (grp_first) wait(smem_u32(&ctl->p_empty[pslot]), (((uint32_t)f >> 1) & 1u) ^ 1u, p, DSITE_PEMPTY);
                             DPROF_ADD(mw_pempty, mt);
                             tc_fence_after();
+                            if (p.trace != nullptr && lane == 0 && mine == 0 && f == 0 && c == 0 && k == kb) p.trace[blockIdx.x * 48 + 3] = globaltimer_ns();
                             if (elect_one()) {
-                                const uint32_t a_base = tmem + aslot * 128;
+                                const uint32_t a_base = tmem + aslot * kACols;
                                 const uint32_t d_base = tmem + kPCol0 + pslot * kPCols;
                                 if (!(p.ablate & 1))
 #pragma unroll
@@ -505,12 +572,14 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     } else if (warp == kActWarp) {
         // =============================== activation rows ============================
         // The activation tile of a stage (M rows x 64 k inside a 16-row, 128-byte-swizzled K-major tile) is written
-        // with 16-byte cp.async copies, three stages ahead, instead of a second TMA box: measured on B200
+        // with 16-byte cp.async copies, D stages ahead, instead of a second TMA box: measured on B200
         // (tools/tma_stream_probe.cu) every cp.async.bulk.tensor costs the TMA unit ~160 cycles + ~2.7 per
         // 128-byte row, and a second box per 64-k stage (even with one in-bounds row) costs 18 % of the streaming
         // rate.  Rows >= M of every stage's tile are zeroed once and never written again.
         if (rg.it1 > rg.it0) {
-            constexpr int D = 3;
+            // Copies run D stages ahead of the `full` arrivals; the ring slot of stage i is only free once stage
+            // i - stages has been consumed, which needs its arrival, so D must stay below the ring depth.
+            const int D = min(3, p.stages - 1);
             const int n_it = rg.it1 - rg.it0;
             for (int s2 = 0; s2 < p.stages; ++s2) {
                 uint4* z = reinterpret_cast<uint4*>(smem_gen + (ring + s2 * kStageBytes + kWBytes - smem_base));
@@ -519,17 +588,21 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
             int tile = rg.it0 / p.k_iters;
             int k = rg.it0 - tile * p.k_iters;
-            int stage = 0, astage = 0;
-            uint32_t ephase = 1;
             int nb = 0;                    // scale blocks issued
             int last_blk = -1;
+            // Scales are static like the weights: when this warp also copies them, the first block goes out before
+            // the wait for the previous kernel.
+            if (!kScaleWarpExists && p.static_weights) scale_step(tile, k, nb, last_blk);
+            if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
+            if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
+            int stage = 0, astage = 0;
+            uint32_t ephase = 1;
             const int r0 = lane >> 3, c16 = lane & 7;          // this lane's row (mod 4) and 16-byte chunk
             const uint8_t* a_lane = reinterpret_cast<const uint8_t*>(p.A) + c16 * 16;
             for (int i = 0; i < n_it; ++i) {
-                if (!has_scale_warp(MC)) scale_step(tile, k, nb, last_blk);
+                if (!kScaleWarpExists) scale_step(tile, k, nb, last_blk);
                 wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
                 const uint32_t bt = ring + stage * kStageBytes + kWBytes;
 #pragma unroll
@@ -543,7 +616,9 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (i >= D) {
-                    asm volatile("cp.async.wait_group %0;" ::"n"(D) : "memory");
+                    if (D == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+                    else if (D == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    else asm volatile("cp.async.wait_group 1;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&ctl->full[astage]));
@@ -560,7 +635,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 if (++astage == p.stages) astage = 0;
             }
         }
-    } else if (has_scale_warp(MC) && warp == kScaleWarp) {
+    } else if (kScaleWarpExists && warp == kScaleWarp) {
         // =============================== scale blocks ===============================
         if (rg.it1 > rg.it0) {
             const int n_it = rg.it1 - rg.it0;
@@ -719,29 +794,31 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             DPROF_ADD(aw_epi, at);
             it += ke - kb;
         }
+        if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 6] = globaltimer_ns();
         if (lane == 0 && warp == kApplyWarp0) { DPROF_OUT(40, aw_sc); DPROF_OUT(41, aw_pfull); DPROF_OUT(42, aw_work); DPROF_OUT(43, aw_epi); }
     } else {
-        // ========================= dequantisers + scale + epilogue =====================
+        // ================================ dequantisers ==================================
         const int q = warp & 3;                 // TMEM lane quarter
-        const int sw = warp >> 2;               // 0..3: piece column set, and the field(s) this warp scales
+        const int sw = warp >> 2;               // 0..DQ/4-1: piece column set
         const int L = q * 32 + lane;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t lane4 = (uint32_t)lane * 4;
-        {   // lane-replicated LUT: entry e for lane l at lut + e*256 + l*4
-            uint32_t* lut_gen = reinterpret_cast<uint32_t*>(smem_gen + (lut - smem_base));
-            const int t = threadIdx.x;      // 0..511
-            if (F::LUTN == 256) {
-                const uint32_t v = __ldg(p.table2 + (t & 255));
-                const int half = t >> 8;    // two threads per entry, 16 lanes each
+        {   // lane-replicated LUT (bank == lane, conflict free): every warp fills whole entries, one conflict-free
+            // 128-byte store per entry (value broadcast from the lane that loaded it).
+            constexpr int kEntriesPerWarp = (F::LUTN + kDqWarps - 1) / kDqWarps;
+            static_assert(kEntriesPerWarp <= 32, "one table2 word per lane");
+            const int e0 = warp * kEntriesPerWarp;
+            const int e_mine = e0 + lane;
+            const uint32_t v = (lane < kEntriesPerWarp && e_mine < F::LUTN) ? __ldg(p.table2 + e_mine) : 0u;
 #pragma unroll
-                for (int l = 0; l < 16; ++l) lut_gen[(t & 255) * (kLutStride / 4) + half * 16 + l] = v;
-            } else {
-                const uint32_t v = __ldg(p.table2 + (t & 15));
-                lut_gen[(t & 15) * (kLutStride / 4) + (t >> 4)] = v;   // 16 entries x 32 lanes = 512 threads
+            for (int i = 0; i < kEntriesPerWarp; ++i) {
+                const uint32_t vi = __shfl_sync(0xffffffffu, v, i);
+                if (e0 + i < F::LUTN) sts32(lut + lut_entry_offset(e0 + i, HALF) + lane * 4, vi);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
         }
         if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 1] = globaltimer_ns();
+        // HALF: lane*4 replicated into every byte (operand of code_lane_folded); else lane*4
+        const uint32_t lane4 = HALF ? (uint32_t)lane * 0x04040404u : (uint32_t)lane * 4;
 
         const uint32_t wrow = (uint32_t)L * 128;
         const int xq = L & 7;
@@ -751,7 +828,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         // crossbar is the limiter (16 B of packed words + 32 x 4 B of LUT reads per lane = 640 wavefronts per
         // stage); with every warp on the SAME stage the barrier waits of all warps coincide and the crossbar
         // idles ~1/3 of the time.  Two sets, one stage apart, fill each other's gaps.
-        constexpr int DQG = (BITS == 4) ? 2 : 1;
+        constexpr int DQG = F::DQG;
         const int grp = (DQG == 2) ? (sw >> 1) : 0;
         const int hw = (DQG == 2) ? (sw & 1) : sw;          // position inside the set
         DPROF_DECL(dw_full = 0, dw_aempty = 0, dw_piece = 0, dw_st = 0);
@@ -788,12 +865,15 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 }
                 DPROF_ADD(dw_aempty, dt);
                 tc_fence_after();
-                const uint32_t tcol = tmem + lane_sel + aslot * 128;
+                const uint32_t tcol = tmem + lane_sel + aslot * kACols;
                 if (do_dq) {
-                    if constexpr (BITS == 4) {
+                    if constexpr (BITS == 4 && !HALF) {
                         // this warp's 16 k-pairs of the stage: 16-byte quads 4*hw .. 4*hw + 3 of row L
-                        Piece<4>::run(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
-                        Piece<4>::run(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
+                        Piece<4>::run<false, CK2>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
+                        Piece<4>::run<false, CK2>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
+                    } else if constexpr (BITS == 4) {
+                        // half stage c: this warp's 8 k-pairs are the 16-byte quads 4*c + 2*hw and 4*c + 2*hw + 1 of row L
+                        Piece<4>::run<true, CK2>(row, (4 * c + 2 * hw) ^ xq, (4 * c + 2 * hw + 1) ^ xq, lut, lane4, tcol + hw * 8);
                     } else {
                         // half stage c: quad c*4 + sw
                         Piece<2>::run(row, (c * 4 + hw) ^ xq, lut, lane4, tcol + hw * 4);
@@ -828,13 +908,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 7] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(tmem, F::TMEM_COLS);
     }
 }
 
-template <int BITS, bool BF16, int MC>
+template <int BITS, bool BF16, int MC, bool HALF>
 static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
-    using F = DCfg<BITS>;
+    using F = DCfg<BITS, HALF>;
     constexpr int TN = F::NJ * 128;
     DecodeParams p{};
     p.A = static_cast<const uint16_t*>(a.A);
@@ -844,6 +924,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.workspace = static_cast<uint8_t*>(a.workspace);
     p.diag = a.diag;
     p.trace = a.trace;
+    p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.G = a.K / a.group_size;
     p.tile_p = a.tile_p;
@@ -853,11 +934,11 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
     p.ablate = a.ablate;
     p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
+    p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : (HALF ? 6 : 0);
 
-    const uint32_t fixed = kScSlots * TN * 16 + F::LUTN * kLutStride + sizeof(Ctl) + 1024 /*alignment slack*/;
-    const uint32_t smem_budget = 232448u;
-    int stages = (int)((smem_budget - fixed) / kStageBytes);
-    if (stages > kMaxStages) stages = kMaxStages;
+    const uint32_t fixed = F::SC_SLOTS * TN * 16 + F::LUTB + sizeof(Ctl) + 1024 /*alignment slack*/;
+    int stages = (int)((F::SMEM_BUDGET - fixed) / kStageBytes);
+    if (stages > F::MAX_STAGES) stages = F::MAX_STAGES;
     if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
     if (stages < 2) return FB_ERR_INTERNAL;
     p.stages = stages;
@@ -865,6 +946,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
     const long long total = (long long)p.n_tiles * p.k_iters;
     if (total > 0x3fffffffLL) return FB_ERR_SHAPE;
+    // HALF: still ONE CTA per SM of this launch -- the other half of each SM is for the next launch's CTAs (PDL).
     int grid = a.num_sms;
     if (a.force_grid > 0) grid = a.force_grid;
     if (grid > total) grid = (int)total;
@@ -879,18 +961,17 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, 64, 128,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
-    auto kern = qgemm_decode_kernel<BITS, BF16, MC>;
-    static bool attr_set[64] = {};
-    if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
-            cudaGetLastError();
-            return FB_ERR_LAUNCH;
-        }
-        attr_set[a.device] = true;
+    auto kern = qgemm_decode_kernel<BITS, BF16, MC, HALF>;
+    // (re-applied on every launch: both calls only store a value in the function's attribute block, and an
+    // unsynchronised "already set" cache would race between host threads)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM_BUDGET) != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_LAUNCH;
     }
+    if (HALF) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads_for(MC));
+    cfg.blockDim = dim3(threads_for(F::DQ, MC, HALF));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[1];
@@ -911,10 +992,16 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 }
 
 template <int BITS, bool BF16>
-static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
-    if (a.M == 1) return launch_t<BITS, BF16, 1>(a, stream);
-    if (a.M <= 4) return launch_t<BITS, BF16, 4>(a, stream);
-    if constexpr (BITS == 4) return launch_t<BITS, BF16, 16>(a, stream);
+static int launch_mc(const QgemmArgs& a, cudaStream_t stream, bool half) {
+    if constexpr (BITS == 4) {
+        if (half && a.M <= 4) {
+            if (a.M == 1) return launch_t<4, BF16, 1, true>(a, stream);
+            return launch_t<4, BF16, 4, true>(a, stream);
+        }
+    }
+    if (a.M == 1) return launch_t<BITS, BF16, 1, false>(a, stream);
+    if (a.M <= 4) return launch_t<BITS, BF16, 4, false>(a, stream);
+    if constexpr (BITS == 4) return launch_t<BITS, BF16, 16, false>(a, stream);
     return FB_ERR_INTERNAL;
 }
 
@@ -930,9 +1017,18 @@ bool qgemm_decode_supported(const QgemmArgs& a) {
     return (a.num_bits == 4 || a.num_bits == 2) && a.M <= m_max;
 }
 
+// Footprint: variant 3 = half-SM, variant 4 = full-SM, otherwise the engine's choice.
+bool qgemm_decode_half_footprint(const QgemmArgs& a) {
+    if (a.num_bits != 4 || a.M > 4) return false;
+    if (a.variant == 3) return true;
+    if (a.variant == 4) return false;
+    return false;
+}
+
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream) {
-    if (a.num_bits == 4) return a.bf16 ? dec::launch_mc<4, true>(a, stream) : dec::launch_mc<4, false>(a, stream);
-    if (a.num_bits == 2) return a.bf16 ? dec::launch_mc<2, true>(a, stream) : dec::launch_mc<2, false>(a, stream);
+    const bool half = qgemm_decode_half_footprint(a);
+    if (a.num_bits == 4) return a.bf16 ? dec::launch_mc<4, true>(a, stream, half) : dec::launch_mc<4, false>(a, stream, half);
+    if (a.num_bits == 2) return a.bf16 ? dec::launch_mc<2, true>(a, stream, false) : dec::launch_mc<2, false>(a, stream, false);
     return FB_ERR_BITS;
 }
 

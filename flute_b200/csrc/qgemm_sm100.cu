@@ -1044,10 +1044,9 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream) {
     // for the cross-kernel-overlap experiments (flute_b200_set_variant(1)).
     // M <= 16, 2/4-bit: the decode kernel (qgemm_decode_sm100.cu) unless a test pins the general kernel
     // (variant 0 / 1, or explicit tiling overrides that only the general kernel understands).
-    if (a.variant == 3 && a.force_mb == 0 && qgemm_decode_lite_supported(a)) return qgemm_decode_lite_launch(a, stream);   // experimental
-    if ((a.variant < 0 || a.variant == 2) && a.force_mb == 0 && qgemm_decode_supported(a)) return qgemm_decode_launch(a, stream);
+    if ((a.variant < 0 || a.variant >= 2) && a.force_mb == 0 && qgemm_decode_supported(a)) return qgemm_decode_launch(a, stream);
     // M > 16, 4-bit: the prefill kernel (qgemm_prefill_sm100.cu)
-    if ((a.variant < 0 || a.variant == 2) && a.force_mb == 0 && qgemm_prefill_supported(a)) return qgemm_prefill_launch(a, stream);
+    if ((a.variant < 0 || a.variant >= 2) && a.force_mb == 0 && qgemm_prefill_supported(a)) return qgemm_prefill_launch(a, stream);
     bool small = false;
     if (a.variant == 1 && (a.num_bits == 4 || a.num_bits == 2) && a.M <= 16) small = true;
     switch (a.num_bits * 4 + (a.bf16 ? 2 : 0) + (small ? 1 : 0)) {

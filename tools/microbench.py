@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--ablate", type=int, default=0)
+    ap.add_argument("--l2pf", type=int, default=-1, help="decode kernel: L2 prefetch distance in stages (-1 = engine's choice)")
     ap.add_argument("--trace", type=int, default=0, help="print a per-CTA timeline of one isolated launch")
     args = ap.parse_args()
 
@@ -48,7 +49,7 @@ def main():
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     ws = utils.get_workspace_streamk(dev)
-    _lib.lib.flute_b200_set_variant((args.variant & 0xff) | (args.ablate << 8))
+    _lib.lib.flute_b200_set_variant((args.variant & 0xff) | (args.ablate << 8) | ((args.l2pf + 1) << 16))
     bits, group = args.bits, args.group
     table = torch.randn(2 ** bits, device=dev).to(dt)
     table2 = utils.make_qmap2_from_qmap(table)
@@ -76,22 +77,30 @@ def main():
                 launch(i)
             torch.cuda.synchronize()
             if args.trace:
-                tr = torch.zeros((256, 48), dtype=torch.int64, device=dev)
-                _lib.lib.flute_b200_set_trace_buffer(tr.data_ptr())
-                launch(1 % ncopies)
+                # three PDL-chained launches, one trace buffer each: shows how far kernel i+1's CTAs get (start, set-up)
+                # while kernel i still runs, and the gap between kernel i's last exit and kernel i+1's first epilogue
+                import numpy as np
+                nchain = 3
+                trs = [torch.zeros((512, 48), dtype=torch.int64, device=dev) for _ in range(nchain)]
+                torch.cuda.synchronize()
+                for j in range(nchain):
+                    _lib.lib.flute_b200_set_trace_buffer(trs[j].data_ptr())
+                    launch((1 + j) % ncopies)
                 torch.cuda.synchronize()
                 _lib.lib.flute_b200_set_trace_buffer(None)
-                t = tr.cpu().numpy()
-                t = t[t[:, 0] > 0]
-                t0 = t[:, 0].min()
-                names = ["start", "setup", "1st-tile", "mma-issued", "acc-full", "epilogue", "fixup", "exit"]
-                import numpy as np
-                print(f"   trace N={N} K={K} M={M}: {t.shape[0]} CTAs; columns = ns since first CTA start (min / median / max)")
-                for c, nm in enumerate(names):
-                    col = t[:, c]; col = col[col > 0] - t0
-                    if col.size:
-                        print(f"     {nm:10s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}   (n={col.size})")
-                if os.environ.get("FLUTE_B200_PROFILE") == "1" and M <= 16 and bits in (2, 4) and args.variant < 0:
+                names = ["start", "setup", "dep-ready", "mma-first", "acc-full", "epilogue", "last-epi", "exit"]
+                t0 = None
+                for j in range(nchain):
+                    t = trs[j].cpu().numpy()
+                    t = t[t[:, 0] > 0]
+                    if t0 is None:
+                        t0 = t[:, 0].min()
+                    print(f"   trace launch {j} N={N} K={K} M={M}: {t.shape[0]} CTAs; ns since the first CTA of launch 0 started (min / median / max)")
+                    for c, nm in enumerate(names):
+                        col = t[:, c]; col = col[col > 0] - t0
+                        if col.size:
+                            print(f"     {nm:10s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}   (n={col.size})")
+                if os.environ.get("FLUTE_B200_PROFILE") == "1" and M <= 16 and bits in (2, 4) and (args.variant < 0 or args.variant >= 2):
                     prof = [(8, "producer scale blocks"), (9, "producer wait-empty"), (10, "producer W issue"),
                             (12, "producer iters"), (13, "mma wait-full"), (14, "mma wait-afull"), (15, "mma wait-pempty"),
                             (16, "mma issue+commit"),
