@@ -74,6 +74,35 @@ def _build(lib_path: str, verbose: bool, extra: list, objname: str) -> str:
     return lib_path
 
 
+TORCH_LIB = os.path.join(HERE, "_flute_b200_torch.so")
+TORCH_SRC = os.path.join(CSRC, "torch_binding.cpp")
+
+
+def build_torch_binding(force: bool = False, verbose: bool = False) -> str:
+    """The compiled torch-operator binding (TORCH_LIBRARY(flute) over the C ABI): one host-only C++ file, g++."""
+    build(False, verbose)
+    deps = [TORCH_SRC, LIB, os.path.join(HERE, "..", "include", "flute_b200.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(TORCH_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(TORCH_LIB) for d in deps):
+        return TORCH_LIB
+    import torch
+    from torch.utils import cpp_extension
+    libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-fPIC", "-shared", "-fvisibility=hidden",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+    for inc in cpp_extension.include_paths("cuda"):
+        cmd += ["-isystem", inc]
+    cmd += [TORCH_SRC, "-o", TORCH_LIB, f"-L{libdir}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+            f"-L{HERE}", "-lflute_b200", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{libdir}"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"torch binding build failed:\n{res.stdout}")
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, profile="--profile" in sys.argv)
     print(path)
+    if "--torch" in sys.argv:
+        print(build_torch_binding(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

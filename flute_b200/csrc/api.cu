@@ -1,6 +1,7 @@
 // C ABI of flute_b200 (declared in include/flute_b200.h): argument validation, device / stream
 // handling, error reporting.  No torch types, no allocation on the hot path, no host sync.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -32,6 +33,7 @@ struct DeviceState {
     fb::Diag* diag_dev = nullptr;
 };
 DeviceState g_dev[kMaxDevices];
+std::mutex g_dev_mutex;                    // guards the lazy per-device initialisation below
 long g_timeout_ms = 10000;
 unsigned long long* g_trace = nullptr;
 int g_ablate = 0;
@@ -55,6 +57,7 @@ struct DeviceGuard {
 int probe_device(int device) {
     if (device < 0 || device >= kMaxDevices) return fail(FB_ERR_DEVICE, "device index %d out of range", device);
     DeviceState& d = g_dev[device];
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
     if (d.probed) return FB_OK;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
@@ -71,6 +74,7 @@ int probe_device(int device) {
 // Lazily create the mapped diagnostics block -- never while a stream capture is in flight.
 fb::Diag* diag_for(int device, cudaStream_t stream) {
     DeviceState& d = g_dev[device];
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
     if (d.diag_dev != nullptr) return d.diag_dev;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -290,10 +294,20 @@ int flute_b200_check(int device) {
     if (device < 0 || device >= kMaxDevices) return fail(FB_ERR_DEVICE, "device index %d out of range", device);
     fb::Diag* d = g_dev[device].diag_host;
     if (d == nullptr || d->code == 0) return FB_OK;
-    static const char* sites[] = {"?", "producer:empty", "dequant:full", "dequant:a_empty", "dequant:scale",
-                                  "dequant:acc_full", "mma:full", "mma:a_full", "mma:acc_empty", "scale:empty", "final"};
+    // sites 1-10: general kernel (ptx.cuh DiagSite); 21-28: decode kernel (DSITE_*); 41-48: prefill kernel (PSITE_*)
+    static const char* general[] = {"?", "producer:empty", "dequant:full", "dequant:a_empty", "dequant:scale",
+                                    "dequant:acc_full", "mma:full", "mma:a_full", "mma:acc_empty", "scale:empty", "final"};
+    static const char* decode[] = {"decode/dequant:full", "decode/dequant:a_empty", "decode/apply:group_sums",
+                                   "decode/apply:scales_full", "decode/producer|activations:empty", "decode/scales:empty",
+                                   "decode/mma:a_full", "decode/mma:p_empty"};
+    static const char* prefill[] = {"prefill/dequant:full", "prefill/dequant:a_slot", "prefill/epilogue:acc_full",
+                                    "prefill/dequant:scales_full", "prefill/producer:empty", "prefill/scales:empty",
+                                    "prefill/mma:a_full", "prefill/mma:acc_empty"};
     int site = d->site;
-    const char* name = (site >= 0 && site <= 10) ? sites[site] : "?";
+    const char* name = "?";
+    if (site >= 0 && site <= 10) name = general[site];
+    else if (site >= 21 && site <= 28) name = decode[site - 21];
+    else if (site >= 41 && site <= 48) name = prefill[site - 41];
     int rc = fail(FB_ERR_KERNEL, "kernel barrier timeout: block %d warp %d waiting at %s(site %d)[%d] parity %d iter %d", d->block,
                   d->warp, name, site, d->index, d->parity, d->iter);
     d->code = 0;

@@ -25,17 +25,21 @@
 //     "group sums ready" at once.
 //
 // Two footprints of the SAME kernel (template parameter HALF; not a fork):
-//   HALF = false  one CTA per SM: 16 dequantiser warps (two sets, one stage apart), 214 KB shared memory,
-//                 512 TMEM columns.
-//   HALF = true   (4-bit, M <= 4) half an SM: 8 dequantiser warps, 512 threads / <= 64 registers, <= 113 KB of
-//                 shared memory (32 KB LUT in a folded layout, 3 ring stages), 256 TMEM columns, grid = #SMs.
-//                 Two such CTAs fit on an SM, so with programmatic dependent launch the NEXT qgemm's CTAs are
-//                 resident while this one still streams: their set-up (barriers, TMEM, LUT), the tensor-map
-//                 fetch, their first weight tiles (static weights) and an L2 prefetch of the tiles after those run
-//                 under this kernel's stream instead of costing ~7 us per launch.
+//   HALF = false  one CTA per SM: 214 KB shared memory (64 KB LUT at a 256-byte entry stride, 9-stage ring),
+//                 <= 80 registers per thread.
+//   HALF = true   (4-bit, M <= 4) the same 16 dequantiser warps and the same 512 TMEM columns, but at most HALF of
+//                 the SM's shared memory (32 KB LUT in a folded layout, 3-stage ring topped up by an L2 prefetch
+//                 stream, 2 scale slots) and <= 40 registers per thread, grid = #SMs.  Two such CTAs fit on an SM, so
+//                 with programmatic dependent launch the NEXT qgemm's CTA is resident while this one still streams:
+//                 its launch latency, barrier set-up, LUT build, tensor-map fetch, its first weight tiles (static
+//                 weights) and the L2 prefetch of the tiles after those all run under this kernel's stream instead
+//                 of costing ~7 us per launch.  Tensor memory is the one thing two CTAs
+//                 cannot share: the newcomer's tcgen05.alloc simply blocks until this CTA frees its columns at exit
+//                 (only the TMEM users -- dequantisers, MMA issuers, apply warps -- wait for it; the producer, the
+//                 activation and the scale warps do not).
 //
 // Warp roles (persistent over a contiguous Stream-K range of (tile, k) stages).  DQ = dequantiser warps
-// (16, HALF: 8); 800 threads for M <= 4, 896 for the opt-in 5 <= M <= 16 variant, 512 for HALF:
+// (16); 800 threads for M <= 4 (HALF: 768), 896 for the opt-in 5 <= M <= 16 variant:
 //   warps 0..DQ-1    dequantisers: warp w owns TMEM lane quarter w%4 and a fixed set of 16-byte quads of its row
 //   warp DQ          TMA producer (packed weights, one 128-row x 64-k box per stage; optional L2 prefetch ahead)
 //   warps DQ+1,DQ+3  tcgen05.mma issuers (alternate scale groups; warp DQ+1 also allocates TMEM)
@@ -77,8 +81,8 @@ struct DCfg<4, false> {
 };
 template <>
 struct DCfg<4, true> {
-    static constexpr int NJ = 4, CK2 = 16, CPS = 2, LUTN = 256, A_SLOTS = 2, P_SLOTS = 2;
-    static constexpr int DQ = 8, DQG = 1, SC_SLOTS = 2, MAX_STAGES = 4, TMEM_COLS = 256, LUTB = 256 * 128;
+    static constexpr int NJ = 4, CK2 = 32, CPS = 1, LUTN = 256, A_SLOTS = 3, P_SLOTS = 2;
+    static constexpr int DQ = 16, DQG = 2, SC_SLOTS = 2, MAX_STAGES = 4, TMEM_COLS = 512, LUTB = 256 * 128;
     static constexpr uint32_t SMEM_BUDGET = 115712u;      // (228 KB - 2 x 1 KB reserved) / 2: two CTAs per SM
 };
 template <>
@@ -90,7 +94,8 @@ struct DCfg<2, false> {
 
 // apply warps: 4 (each all NJ fields) for M <= 4; 8 (two field halves) when a field needs 16 accumulators
 __host__ __device__ constexpr int apply_warps(int mc) { return mc > 4 ? 8 : 4; }
-// full footprint, M <= 4: one more warp copies the scale blocks; otherwise the activation warp does
+// full footprint, M <= 4: one more warp copies the scale blocks; otherwise the activation warp does (HALF: 24 warps,
+// so that two CTAs x 768 threads get 40 registers each -- a 25th warp rounds the allocation down to 32)
 __host__ __device__ constexpr bool has_scale_warp(int mc, bool half) { return mc <= 4 && !half; }
 __host__ __device__ constexpr int threads_for(int dq, int mc, bool half) {
     return (dq + 4 + apply_warps(mc) + (has_scale_warp(mc, half) ? 1 : 0)) * 32;
@@ -111,6 +116,7 @@ struct Ctl {
     uint64_t p_empty[2];
     uint64_t sc_full[kMaxScSlots];
     uint64_t sc_empty[kMaxScSlots];
+    uint64_t tmem_ready;     // the allocating warp arrives once the TMEM base address is in tmem_base
     uint32_t tmem_base;
     int is_last;
 };
@@ -305,6 +311,27 @@ struct Piece<4> {
         for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * FSTRIDE, r[j]);
     }
 };
+// Register-lean form for the co-resident footprint (<= 40 registers per thread): ONE 16-byte quad (4 k-pairs) of row L
+// -> 4 fields x 4 TMEM columns, through the folded LUT.  `w` was loaded by the caller one call ahead.
+struct Piece4Lean {
+    template <int FSTRIDE>
+    static __device__ __forceinline__ void run(const uint4& v, uint32_t lut, uint32_t lane4rep, uint32_t tcol) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t r[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t w7 = w[i] & 0x7f7f7f7fu;
+            uint32_t x;      // (w & 0x80808080) | lane*4 in every byte
+            asm("lop3.b32 %0, %1, 0x80808080, %2, 0xEA;" : "=r"(x) : "r"(w[i]), "r"(lane4rep));
+            r[0][i] = lds32(lut + code_lane_folded<0>(w7, x));
+            r[1][i] = lds32(lut + code_lane_folded<1>(w7, x));
+            r[2][i] = lds32(lut + code_lane_folded<2>(w7, x));
+            r[3][i] = lds32(lut + code_lane_folded<3>(w7, x));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_st_x4(tcol + j * FSTRIDE, r[j][0], r[j][1], r[j][2], r[j][3]);
+    }
+};
 template <>
 struct Piece<2> {
     static __device__ __forceinline__ void run(uint32_t row, int pq, uint32_t lut, uint32_t lane4, uint32_t tcol) {
@@ -397,19 +424,27 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             mbar_init(smem_u32(&ctl->sc_full[s]), 32);   // one (deferred) arrival per lane of the activation/scale warp
             mbar_init(smem_u32(&ctl->sc_empty[s]), kApplyWarps);
         }
+        mbar_init(smem_u32(&ctl->tmem_ready), 1);
         mbar_fence_init();
     }
+    // First sync: barriers visible.  The producer starts streaming right after it, the dequant warps build the LUT;
+    // tensor memory is allocated AFTER it by one warp, and only the TMEM users wait for the address (tmem_ready):
+    // when the previous launch's CTA still holds this SM's columns (HALF, co-resident under PDL) the allocation
+    // blocks until that CTA exits, and everything that does not touch TMEM proceeds meanwhile.
+    __syncthreads();
+    pdl_launch_dependents();
     if (warp == kMmaWarp) {
         tmem_alloc(smem_u32(&ctl->tmem_base), F::TMEM_COLS);
         tmem_relinquish();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_ready));
     }
-    // First sync: barriers + TMEM address visible; the producer starts streaming right after it while the
-    // dequant warps are still building the LUT (second, dequant-only sync below).
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = ctl->tmem_base;
-    pdl_launch_dependents();
+    auto tmem_base_when_ready = [&]() -> uint32_t {
+        wait(smem_u32(&ctl->tmem_ready), 0u, p, DSITE_AFULL, -1);
+        tc_fence_after();
+        return *reinterpret_cast<volatile uint32_t*>(&ctl->tmem_base);
+    };
 
     // One step of the scale-block schedule (called once per stage, in stage order, by ONE warp): when stage (tile, k)
     // starts a new block of 8 groups, copy [tile columns] x [8 groups] (16 bytes per row) into the next scale slot.
@@ -479,7 +514,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     const uint32_t bar = smem_u32(&ctl->full[stage]);
                     mbar_arrive_expect_tx(bar, kWBytes);
                     tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, tile * 128, pol_w);
-                    const int pf_end = min(n_it, i + 1 + pf_ahead);
+                    const int pf_end = pf_ahead > 0 ? min(n_it, i + 1 + pf_ahead) : 0;
                     while (pf_i < pf_end) {       // first iterations: catch up; steady state: one box per stage
                         tma_prefetch_l2_2d(&tmap_w, pf_k * 64, pf_tile * 128);
                         ++pf_i;
@@ -503,6 +538,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         // tools/mma_rate_probe.cu), which made it the slowest role of the pipeline.
         if (rg.it1 > rg.it0) {
             const int mine = (warp == kMmaWarp) ? 0 : 1;
+            const uint32_t tmem = tmem_base_when_ready();
             const uint32_t idesc = make_idesc_f16(BF16, 128, kMb);
             int stage = 0;
             int aslot = 0;
@@ -657,6 +693,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 #pragma unroll
         for (int j = 0; j < NFA; ++j) nloc[j] = n_local<BITS, NJ>(L, fset * NFA + j, p.tile_p);
         const bool do_apply = !(p.ablate & 4);
+        const uint32_t tmem = (rg.it1 > rg.it0) ? tmem_base_when_ready() : 0u;
         int pslot = 0;
         int stage = 0;                     // ring slot / phase of the stage the loop is at
         uint32_t dphase = 0;
@@ -817,6 +854,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
         }
         if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 1] = globaltimer_ns();
+        const uint32_t tmem = (rg.it1 > rg.it0) ? tmem_base_when_ready() : 0u;
         // HALF: lane*4 replicated into every byte (operand of code_lane_folded); else lane*4
         const uint32_t lane4 = HALF ? (uint32_t)lane * 0x04040404u : (uint32_t)lane * 4;
 
@@ -872,8 +910,15 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         Piece<4>::run<false, CK2>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
                         Piece<4>::run<false, CK2>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
                     } else if constexpr (BITS == 4) {
-                        // half stage c: this warp's 8 k-pairs are the 16-byte quads 4*c + 2*hw and 4*c + 2*hw + 1 of row L
-                        Piece<4>::run<true, CK2>(row, (4 * c + 2 * hw) ^ xq, (4 * c + 2 * hw + 1) ^ xq, lut, lane4, tcol + hw * 8);
+                        // same 4 quads, 16 look-ups at a time (<= 40 registers), each quad's words loaded one call ahead
+                        uint4 va = lds128(row + (uint32_t)(((4 * hw) ^ xq) << 4));
+                        uint4 vb = lds128(row + (uint32_t)(((4 * hw + 1) ^ xq) << 4));
+                        Piece4Lean::run<CK2>(va, lut, lane4, tcol + hw * 16);
+                        va = lds128(row + (uint32_t)(((4 * hw + 2) ^ xq) << 4));
+                        Piece4Lean::run<CK2>(vb, lut, lane4, tcol + hw * 16 + 4);
+                        vb = lds128(row + (uint32_t)(((4 * hw + 3) ^ xq) << 4));
+                        Piece4Lean::run<CK2>(va, lut, lane4, tcol + hw * 16 + 8);
+                        Piece4Lean::run<CK2>(vb, lut, lane4, tcol + hw * 16 + 12);
                     } else {
                         // half stage c: quad c*4 + sw
                         Piece<2>::run(row, (c * 4 + hw) ^ xq, lut, lane4, tcol + hw * 4);
@@ -908,7 +953,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 7] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        tmem_dealloc(tmem, F::TMEM_COLS);
+        tmem_dealloc(*reinterpret_cast<volatile uint32_t*>(&ctl->tmem_base), F::TMEM_COLS);
     }
 }
 
@@ -962,13 +1007,15 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
     auto kern = qgemm_decode_kernel<BITS, BF16, MC, HALF>;
-    // (re-applied on every launch: both calls only store a value in the function's attribute block, and an
-    // unsynchronised "already set" cache would race between host threads)
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM_BUDGET) != cudaSuccess) {
-        cudaGetLastError();
-        return FB_ERR_LAUNCH;
+    static PerDeviceOnce attr_set;      // one per template instantiation
+    if (!attr_set.done(a.device)) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM_BUDGET) != cudaSuccess) {
+            cudaGetLastError();
+            return FB_ERR_LAUNCH;
+        }
+        if (HALF) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set.mark(a.device);
     }
-    if (HALF) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads_for(F::DQ, MC, HALF));

@@ -86,6 +86,7 @@ struct Params {
     uint8_t* workspace;
     Diag* diag;
     unsigned long long* trace;
+    unsigned long long timeout_ns;   // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
     int M, N, K, G;
     int tile_p;
     int gshift;
@@ -116,10 +117,10 @@ __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const Params
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0) {
+        if ((++spins & 0x3ff) == 0 && p.timeout_ns != 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // 4 s: trap, don't hang
+            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
         }
     }
 }
@@ -598,6 +599,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.workspace = static_cast<uint8_t*>(a.workspace);
     p.diag = a.diag;
     p.trace = a.trace;
+    p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.G = a.K / a.group_size;
     p.tile_p = a.tile_p;
@@ -622,19 +624,22 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     int grid = a.num_sms;
     if (a.force_grid > 0) grid = a.force_grid;
     // whole tiles per CTA unless that leaves more than ~10 % of the machine idle in the last wave
+    constexpr size_t kCounterBytes = 65536;
     {
         const long long waves = (tiles + grid - 1) / grid;
         p.streamk = (tiles * 10 < waves * grid * 9) ? 1 : 0;
     }
     if (a.force_streamk >= 0) p.streamk = a.force_streamk;
+    // Stream-K needs one arrival counter per tile in the 64 KB counter region; beyond that (very large M x N, where
+    // the last-wave loss is negligible anyway) every CTA takes whole tiles and no counter is touched.
+    if ((size_t)tiles * 4 > kCounterBytes) p.streamk = 0;
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
 
     // workspace: [tile counters: fixed 64 KB, zero between launches][... zero-invariant fp32 accumulators of the
     // other kernels ...][2 partial-tile slots per CTA at the very end, contents undefined between launches]
-    constexpr size_t kCounterBytes = 65536;
     const size_t scratch = prefill_scratch_bytes(a.num_sms);
-    if ((size_t)tiles * 4 > kCounterBytes || a.workspace_bytes < kCounterBytes + scratch || grid > a.num_sms) return FB_ERR_WORKSPACE;
+    if (a.workspace_bytes < kCounterBytes + scratch || grid > a.num_sms) return FB_ERR_WORKSPACE;
     p.scratch_offset = (a.workspace_bytes - scratch) & ~(size_t)255;
 
     CUtensorMap tm_w, tm_a;
@@ -646,13 +651,13 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
                       (uint64_t)a.M, (uint64_t)a.K * 2, 64, kMb, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
     auto kern = qgemm_prefill_kernel<BF16>;
-    static bool attr_set[64] = {};
-    if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done(a.device)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
             cudaGetLastError();
             return FB_ERR_LAUNCH;
         }
-        attr_set[a.device] = true;
+        attr_set.mark(a.device);
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

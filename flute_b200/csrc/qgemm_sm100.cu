@@ -886,20 +886,50 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static PFN_encodeTiled lookup_encode_fn() {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<PFN_encodeTiled>(ptr);
+    return nullptr;
+}
 static PFN_encodeTiled get_encode_fn() {
-    static PFN_encodeTiled fn = nullptr;
-    if (fn == nullptr) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-    }
+    static const PFN_encodeTiled fn = lookup_encode_fn();   // C++11 magic static: initialised once, thread-safe
     return fn;
 }
 
+// Eager callers (one qgemm per Python call) would otherwise pay a cuTensorMapEncodeTiled per launch; the descriptor
+// is a pure function of these eight values, so a small per-thread direct-mapped cache returns it.
+namespace {
+struct TmapKey {
+    const void* base;
+    uint64_t inner, outer, row_bytes;
+    uint32_t box_inner, box_outer;
+    int dt, swizzle;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && row_bytes == o.row_bytes &&
+               box_inner == o.box_inner && box_outer == o.box_outer && dt == o.dt && swizzle == o.swizzle;
+    }
+};
+struct TmapSlot {
+    TmapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+constexpr int kTmapSlots = 256;
+thread_local TmapSlot t_tmap_cache[kTmapSlots];
+}  // namespace
+
 int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                  uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
+    const TmapKey key{base, inner, outer, row_bytes, box_inner, box_outer, (int)dt, (int)swizzle};
+    const uint64_t h = (reinterpret_cast<uint64_t>(base) >> 8) * 0x9E3779B97F4A7C15ull + outer * 31 + box_outer;
+    TmapSlot& slot = t_tmap_cache[(h >> 40) & (kTmapSlots - 1)];
+    if (slot.valid && slot.key == key) {
+        *tm = slot.map;
+        return FB_OK;
+    }
     PFN_encodeTiled enc = get_encode_fn();
     if (enc == nullptr) return FB_ERR_DRIVER;
     cuuint64_t dims[2] = {inner, outer};
@@ -908,7 +938,11 @@ int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? FB_OK : FB_ERR_TENSORMAP;
+    if (r != CUDA_SUCCESS) return FB_ERR_TENSORMAP;
+    slot.key = key;
+    slot.map = *tm;
+    slot.valid = true;
+    return FB_OK;
 }
 
 int make_tmap_3d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
@@ -1005,14 +1039,14 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (rc != FB_OK) return rc;
 
     auto kern = qgemm_sm100_kernel<BITS, BF16, SMALL>;
-    static bool attr_set[64] = {};
-    if (a.device >= 0 && a.device < 64 && !attr_set[a.device]) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done(a.device)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget) != cudaSuccess) {
             cudaGetLastError();
             return FB_ERR_LAUNCH;
         }
         if (SMALL) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set[a.device] = true;
+        attr_set.mark(a.device);
     }
 
     cudaLaunchConfig_t cfg{};

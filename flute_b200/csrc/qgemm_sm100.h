@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -65,6 +66,14 @@ struct QgemmParams {
     int static_weights;       // weights may be prefetched before griddepcontrol.wait
     uint32_t neg_zero2;       // packed (-0, -0): addend that keeps the scale multiply an FMA-pipe instruction
     uint32_t plane1_row0;     // 3-bit: first row of planes 1/2 (N/16)
+};
+
+// "Function attribute already set on this device" bits, safe against concurrent first calls from several host
+// threads (setting an attribute twice is harmless; a torn bool array is not).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool done(int device) const { return device >= 0 && device < 64 && ((mask.load(std::memory_order_acquire) >> device) & 1ull); }
+    void mark(int device) { if (device >= 0 && device < 64) mask.fetch_or(1ull << device, std::memory_order_release); }
 };
 
 int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);

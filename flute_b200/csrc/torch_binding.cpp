@@ -1,0 +1,142 @@
+// Compiled torch-operator binding over the C ABI of libflute_b200.so.
+//
+// Same job as the op registration of the reference (flute/csrc/qgemm.cpp:86-198 `qgemm_raw_simple`, :201-244
+// `apply_hadamard` / `qgemm_raw_simple_hadamard`, :251-260 TORCH_LIBRARY / TORCH_LIBRARY_IMPL): the schemas are the
+// reference's, the bodies only validate, extract pointers, pick the current device / stream and make ONE C-ABI call.
+// No CUDA code lives here and nothing is computed on the host; a non-zero return code becomes a c10::Error carrying
+// flute_b200_last_error() (the reference raises through AT_ERROR / C10_CUDA_KERNEL_LAUNCH_CHECK, qgemm.cpp:82,153,171).
+// Built by flute_b200/build.py into flute_b200/_flute_b200_torch.so (links libflute_b200.so via $ORIGIN).
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/flute_b200.h"
+
+namespace {
+
+std::atomic<int> g_launch_flags{-1};
+
+int env_flags() {
+    const char* pdl = std::getenv("FLUTE_B200_PDL");
+    const char* stat = std::getenv("FLUTE_B200_STATIC_WEIGHTS");
+    int f = (pdl == nullptr || std::strcmp(pdl, "0") != 0) ? FLUTE_B200_FLAG_PDL : 0;
+    if (f != 0 && stat != nullptr && std::strcmp(stat, "1") == 0) f |= FLUTE_B200_FLAG_STATIC_WEIGHTS;
+    return f;
+}
+
+int launch_flags() {
+    int f = g_launch_flags.load(std::memory_order_relaxed);
+    if (f < 0) {
+        f = env_flags();
+        g_launch_flags.store(f, std::memory_order_relaxed);
+    }
+    return f;
+}
+
+// TileP of template (num_bits, template_id): the enumeration of flute/codegen_utils.py:89-160 in closed form
+// (3 SM multiples x 3 tile shapes {TileP 64, 32, 32} x 4 stage counts x {4 quant-map modes at 4 bits, else 1}).
+int tile_p_of(int64_t num_bits, int64_t template_id) {
+    const int64_t per_tile = 4 * (num_bits == 4 ? 4 : 1);
+    TORCH_CHECK(template_id >= 0 && template_id < 9 * per_tile, "Unsupported template_id ", template_id,
+                " for num_bits ", num_bits);
+    return ((template_id / per_tile) % 3) == 0 ? 64 : 32;
+}
+
+int dtype_code(const at::Tensor& t) {
+    if (t.scalar_type() == at::kHalf) return FLUTE_B200_F16;
+    if (t.scalar_type() == at::kBFloat16) return FLUTE_B200_BF16;
+    TORCH_CHECK(false, "flute_b200: unsupported dtype ", t.scalar_type(), " (fp16 / bf16 only)");
+}
+
+// The formal input contract of flute/ops.py:17-49, plus what the reference silently assumes (contiguity: it reads
+// raw data_ptr, qgemm.cpp:71).
+void check_inputs(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& scales, const at::Tensor& table,
+                  const at::Tensor& table2, const at::Tensor& workspace, int64_t num_bits, int64_t group_size) {
+    TORCH_CHECK(num_bits == 2 || num_bits == 3 || num_bits == 4, "Unsupported `num_bits` ", num_bits);
+    TORCH_CHECK(input.dim() >= 2 && weight.dim() == 2 && scales.dim() == 2 && table.dim() == 1 && table2.dim() == 3 &&
+                    workspace.dim() == 1, "flute_b200: bad tensor ranks");
+    const auto dt = input.scalar_type();
+    TORCH_CHECK(dt == at::kHalf || dt == at::kBFloat16, "flute_b200: input must be fp16 or bf16");
+    TORCH_CHECK(weight.scalar_type() == at::kShort && scales.scalar_type() == dt && table.scalar_type() == dt &&
+                    table2.scalar_type() == at::kFloat && workspace.scalar_type() == at::kByte, "flute_b200: dtype mismatch");
+    const int64_t levels = int64_t(1) << num_bits;
+    TORCH_CHECK(weight.size(1) == input.size(-1) && weight.size(1) == scales.size(1) * group_size &&
+                    weight.size(0) == (int64_t)(num_bits * (scales.size(0) / 16.0)) && table.size(0) == levels &&
+                    table2.size(0) == levels && table2.size(1) == levels && table2.size(2) == 1,
+                "flute_b200: shape mismatch");
+    for (const at::Tensor* t : {&weight, &scales, &table, &table2, &workspace})
+        TORCH_CHECK(t->is_contiguous() && t->device() == input.device(),
+                    "flute_b200: weight/scales/tables/workspace must be contiguous and on the input's device");
+}
+
+at::Tensor qgemm_raw_simple(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& scales,
+                            const at::Tensor& table, const at::Tensor& table2, at::Tensor& workspace, int64_t num_bits,
+                            int64_t group_size, int64_t template_id, int64_t num_sms) {
+    (void)num_sms;   // accepted for signature compatibility; the engine sizes its grid from the device
+    check_inputs(input, weight, scales, table, table2, workspace, num_bits, group_size);
+    const c10::cuda::OptionalCUDAGuard guard(input.device());
+    const int64_t K = input.size(-1), N = scales.size(0);
+    at::Tensor x = input.reshape({-1, K});
+    if (!x.is_contiguous()) x = x.contiguous();
+    const int64_t M = x.size(0);
+    at::Tensor out = at::empty({M, N}, input.options());
+    if (M > 0) {
+        const int rc = flute_b200_qgemm(x.data_ptr(), weight.data_ptr(), out.data_ptr(), scales.data_ptr(), table.data_ptr(),
+                                        table2.data_ptr(), workspace.data_ptr(), (size_t)workspace.numel(), (int)M, (int)N,
+                                        (int)K, (int)num_bits, (int)group_size, tile_p_of(num_bits, template_id),
+                                        dtype_code(input), launch_flags(), (int)input.get_device(),
+                                        at::cuda::getCurrentCUDAStream().stream());
+        TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
+    }
+    auto sizes = input.sizes().vec();
+    sizes.back() = N;
+    return out.reshape(sizes);
+}
+
+at::Tensor hadamard(const at::Tensor& x, int64_t hadamard_size) {
+    TORCH_CHECK(x.scalar_type() == at::kHalf || x.scalar_type() == at::kBFloat16, "Only fp16 and bf16 supported currently");
+    TORCH_CHECK(hadamard_size > 0 && x.size(-1) % hadamard_size == 0,
+                "flute_b200: last dimension must be a multiple of hadamard_size");
+    const c10::cuda::OptionalCUDAGuard guard(x.device());
+    at::Tensor xc = x.is_contiguous() ? x : x.contiguous();
+    at::Tensor out = at::empty_like(xc);
+    if (xc.numel() > 0) {
+        const int rc = flute_b200_hadamard(xc.data_ptr(), out.data_ptr(), (long)(xc.numel() / hadamard_size),
+                                           (int)hadamard_size, dtype_code(x), (int)x.get_device(),
+                                           at::cuda::getCurrentCUDAStream().stream());
+        TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
+    }
+    return out;
+}
+
+at::Tensor qgemm_raw_simple_hadamard(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& scales,
+                                     const at::Tensor& table, const at::Tensor& table2, at::Tensor& workspace,
+                                     int64_t num_bits, int64_t group_size, int64_t hadamard_size, int64_t template_id,
+                                     int64_t num_sms) {
+    return qgemm_raw_simple(hadamard(input, hadamard_size), weight, scales, table, table2, workspace, num_bits, group_size,
+                            template_id, num_sms);
+}
+
+}  // namespace
+
+// Process-wide launch behaviour of flute.qgemm through this binding (mirrors flute_b200.ops.set_launch_flags).
+extern "C" __attribute__((visibility("default"))) void flute_b200_torch_set_launch_flags(int flags) {
+    g_launch_flags.store(flags & (FLUTE_B200_FLAG_PDL | FLUTE_B200_FLAG_STATIC_WEIGHTS), std::memory_order_relaxed);
+}
+
+TORCH_LIBRARY(flute, m) {
+    m.def("qgemm_raw_simple(Tensor input, Tensor weight, Tensor scales, Tensor table, Tensor table2, Tensor(a!) workspace, int num_bits, int group_size, int template_id, int num_sms) -> Tensor");
+    m.def("qgemm_raw_simple_hadamard(Tensor input, Tensor weight, Tensor scales, Tensor table, Tensor table2, Tensor(a!) workspace, int num_bits, int group_size, int hadamard_size, int template_id, int num_sms) -> Tensor");
+    m.def("hadamard_transform(Tensor input, int hadamard_size) -> Tensor");
+}
+
+TORCH_LIBRARY_IMPL(flute, CUDA, m) {
+    m.impl("qgemm_raw_simple", &qgemm_raw_simple);
+    m.impl("qgemm_raw_simple_hadamard", &qgemm_raw_simple_hadamard);
+    m.impl("hadamard_transform", &hadamard);
+}

@@ -1,5 +1,14 @@
 """Torch operator surface: the reference's schemas, verbatim, backed by the C ABI.
 
+Two bindings register `torch.ops.flute.*`; `BINDING` says which one is live:
+  "cpp"     flute_b200/_flute_b200_torch.so -- a compiled TORCH_LIBRARY(flute) / TORCH_LIBRARY_IMPL(flute, CUDA)
+            shim over the C ABI (csrc/torch_binding.cpp; the counterpart of flute/csrc/qgemm.cpp:251-260), a few
+            microseconds of host time per call.  Used whenever it has been built (build.py --torch,
+            __graft_entry__.build()).
+  "python"  the torch.library Python implementation below over ctypes (tens of microseconds per eager call; the
+            same C-ABI call).  Used when the shim is absent or FLUTE_B200_PY_OPS=1.
+Either way the kernels are the ones in libflute_b200.so; neither binding computes anything itself.
+
 Schemas are those of `TORCH_LIBRARY(flute, m)` (flute/csrc/qgemm.cpp:251-254); the fake
 implementations carry the input contract of flute/ops.py:4-83 so torch.compile / opcheck
 behave as they do with the reference.  The CUDA implementations hand raw pointers, the
@@ -36,11 +45,26 @@ def set_launch_flags(pdl: bool = True, static_weights: bool = False) -> None:
     """Process-wide launch behaviour of flute.qgemm (see the comment above)."""
     global LAUNCH_FLAGS
     LAUNCH_FLAGS = (_lib.FLAG_PDL if pdl else 0) | (_lib.FLAG_STATIC_WEIGHTS if (pdl and static_weights) else 0)
+    if _cpp is not None:
+        _cpp.flute_b200_torch_set_launch_flags(LAUNCH_FLAGS)
 
 NAMESPACE = "flute"
+_TORCH_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_flute_b200_torch.so")
+BINDING = "python"
+_cpp = None
 try:
-    torch.library.define(f"{NAMESPACE}::qgemm_raw_simple", _SCHEMA_QGEMM)
-    torch.library.define(f"{NAMESPACE}::qgemm_raw_simple_hadamard", _SCHEMA_QGEMM_HADAMARD)
+    if os.environ.get("FLUTE_B200_PY_OPS", "0") != "1" and os.path.exists(_TORCH_LIB_PATH):
+        import ctypes as _ctypes
+        torch.ops.load_library(_TORCH_LIB_PATH)          # runs TORCH_LIBRARY(flute) + the CUDA impl registration
+        _cpp = _ctypes.CDLL(_TORCH_LIB_PATH)             # same handle: for flute_b200_torch_set_launch_flags
+        _cpp.flute_b200_torch_set_launch_flags.argtypes = [_ctypes.c_int]
+        _cpp.flute_b200_torch_set_launch_flags.restype = None
+        _cpp.flute_b200_torch_set_launch_flags(LAUNCH_FLAGS)
+        BINDING = "cpp"
+    else:
+        torch.library.define(f"{NAMESPACE}::qgemm_raw_simple", _SCHEMA_QGEMM)
+        torch.library.define(f"{NAMESPACE}::qgemm_raw_simple_hadamard", _SCHEMA_QGEMM_HADAMARD)
+        torch.library.define(f"{NAMESPACE}::hadamard_transform", "(Tensor input, int hadamard_size) -> Tensor")
 except RuntimeError as exc:   # the reference's own extension is loaded in this process
     raise ImportError(
         "torch.ops.flute.qgemm_raw_simple is already registered (is the reference `flute` package "
@@ -136,8 +160,10 @@ def _qgemm_hadamard_cuda(input, weight, scales, table, table2, workspace, num_bi
                        group_size, template_id, num_sms)
 
 
-torch.library.impl(f"{NAMESPACE}::qgemm_raw_simple", "CUDA")(_qgemm_cuda)
-torch.library.impl(f"{NAMESPACE}::qgemm_raw_simple_hadamard", "CUDA")(_qgemm_hadamard_cuda)
+if BINDING == "python":
+    torch.library.impl(f"{NAMESPACE}::qgemm_raw_simple", "CUDA")(_qgemm_cuda)
+    torch.library.impl(f"{NAMESPACE}::qgemm_raw_simple_hadamard", "CUDA")(_qgemm_hadamard_cuda)
+    torch.library.impl(f"{NAMESPACE}::hadamard_transform", "CUDA")(hadamard_transform)
 
 
 @torch.library.register_fake(f"{NAMESPACE}::qgemm_raw_simple")
@@ -146,6 +172,11 @@ def _qgemm_raw_simple_abstract(input, weight, scales, table, table2, workspace, 
     _check_inputs(input, weight, scales, table, table2, workspace, num_bits, group_size)
     N = scales.shape[0]
     return torch.empty(input.shape[:-1] + (N,), dtype=input.dtype, device=input.device)
+
+
+@torch.library.register_fake(f"{NAMESPACE}::hadamard_transform")
+def _hadamard_transform_abstract(input, hadamard_size):
+    return torch.empty_like(input, memory_format=torch.contiguous_format)
 
 
 @torch.library.register_fake(f"{NAMESPACE}::qgemm_raw_simple_hadamard")

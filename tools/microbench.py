@@ -83,11 +83,22 @@ def main():
                 nchain = 3
                 trs = [torch.zeros((512, 48), dtype=torch.int64, device=dev) for _ in range(nchain)]
                 torch.cuda.synchronize()
-                for j in range(nchain):
-                    _lib.lib.flute_b200_set_trace_buffer(trs[j].data_ptr())
-                    launch((1 + j) % ncopies)
+                # captured in ONE CUDA graph (eager launches through ctypes are ~10 us apart: host-bound, no overlap to see);
+                # the trace pointer is a kernel argument, fixed at capture time
+                tg = torch.cuda.CUDAGraph()
+                tside = torch.cuda.Stream()
+                with torch.cuda.stream(tside):
+                    with torch.cuda.graph(tg, stream=tside):
+                        launch(0)
+                        for j in range(nchain):
+                            _lib.lib.flute_b200_set_trace_buffer(trs[j].data_ptr())
+                            launch((1 + j) % ncopies)
+                        _lib.lib.flute_b200_set_trace_buffer(None)
+                        launch((1 + nchain) % ncopies)
                 torch.cuda.synchronize()
-                _lib.lib.flute_b200_set_trace_buffer(None)
+                for _ in range(2):
+                    tg.replay()
+                torch.cuda.synchronize()
                 names = ["start", "setup", "dep-ready", "mma-first", "acc-full", "epilogue", "last-epi", "exit"]
                 t0 = None
                 for j in range(nchain):
