@@ -108,7 +108,8 @@ constexpr int kStageBytes = kWBytes + kBBytes;
 constexpr int kMb = 16;              // MMA N
 
 struct Ctl {
-    uint64_t full[kMaxStagesAny];
+    uint64_t full[kMaxStagesAny];       // packed weights of the stage have landed (TMA)
+    uint64_t act_full[kMaxStagesAny];   // activation rows of the stage have landed (cp.async)
     uint64_t empty[kMaxStagesAny];
     uint64_t a_full[3];
     uint64_t a_empty[3];
@@ -123,6 +124,7 @@ struct Ctl {
 
 struct DecodeParams {
     const uint16_t* A;
+    const uint8_t* Q;      // packed weights [P, K] int16 (also behind the tensor map; raw pointer for the entry prefetch)
     const uint16_t* S;
     const uint32_t* table2;
     uint16_t* D;
@@ -131,6 +133,7 @@ struct DecodeParams {
     unsigned long long* trace;
     unsigned long long timeout_ns;   // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
     int M, N, K, G;
+    int P;               // packed rows = N / 16 * bits
     int tile_p;
     int gshift;          // log2(group_size / 64): stages per group
     int n_tiles, k_iters;
@@ -405,11 +408,30 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 
     if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 0] = globaltimer_ns();
     if (!p.static_weights) pdl_wait_prior_grids();
+    // Entry prefetch: the first TMA box cannot be requested before the barriers exist and the tensor map has been
+    // fetched (~1 us after launch), and then pays a cold DRAM + page-walk latency on top.  The row addresses are plain
+    // arithmetic, so every dequantiser thread asks L2 for one 128-byte row piece of the CTA's first ring-full of
+    // stages right away; the TMA loads then hit L2.
+    if (warp < kDqWarps && rg.it1 > rg.it0) {
+        const int npf = min(rg.it1 - rg.it0, p.stages);
+        const int r = threadIdx.x & 127;
+        for (int s0 = threadIdx.x >> 7; s0 < npf; s0 += kDqWarps / 4) {
+            const int it = rg.it0 + s0;
+            const int tile = it / p.k_iters;
+            const int k = it - tile * p.k_iters;
+            const int prow = tile * 128 + r;
+            if (prow < p.P) {
+                const uint8_t* addr = p.Q + ((size_t)prow * p.K + (size_t)k * 64) * 2;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(addr) : "memory");
+            }
+        }
+    }
 
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(smem_u32(&ctl->full[s]), 2);   // TMA (expect_tx) + the activation rows
+            mbar_init(smem_u32(&ctl->full[s]), 1);       // TMA (expect_tx): what the dequantisers wait for
+            mbar_init(smem_u32(&ctl->act_full[s]), 1);   // the activation warp: what the MMA issuers wait for
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
         for (int s = 0; s < AS; ++s) {
@@ -541,6 +563,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             const uint32_t tmem = tmem_base_when_ready();
             const uint32_t idesc = make_idesc_f16(BF16, 128, kMb);
             int stage = 0;
+            uint32_t sphase = 0;           // parity of the ring pass `stage` is in
             int aslot = 0;
             uint32_t aphase = 0;
             int f = 0;                     // flush groups started so far
@@ -554,7 +577,9 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 for (int k = kb; k < ke; ++k) {
                     const bool my_group = ((f & 1) == mine);
                     if (my_group) {
-                        // (no wait on full[stage]: every dequant warp observed it before arriving on a_full)
+                        // The dequantisers only need the weights (full[stage]), so the first A slots fill while the
+                        // previous kernel is still running; the activation rows are what the MMAs themselves wait for.
+                        wait(smem_u32(&ctl->act_full[stage]), sphase, p, DSITE_FULL, 1);
                         const uint64_t bdesc = make_smem_desc_sw128(ring + stage * kStageBytes + kWBytes);
                         const int pslot = mine;
 #pragma unroll
@@ -599,7 +624,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     }
                     const bool flush = (((k + 1) & spg_mask) == 0) || (k == ke - 1);
                     if (flush) { grp_first = true; ++f; }
-                    if (++stage == p.stages) stage = 0;
+                    if (++stage == p.stages) { stage = 0; sphase ^= 1u; }
                 }
                 it += ke - kb;
             }
@@ -657,7 +682,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     else asm volatile("cp.async.wait_group 1;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[astage]));
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->act_full[astage]));
                     if (++astage == p.stages) astage = 0;
                 }
                 if (++stage == p.stages) { stage = 0; ephase ^= 1u; }
@@ -667,7 +692,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             for (int i = max(0, n_it - D); i < n_it; ++i) {
-                if (lane == 0) mbar_arrive(smem_u32(&ctl->full[astage]));
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->act_full[astage]));
                 if (++astage == p.stages) astage = 0;
             }
         }
@@ -803,6 +828,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     for (int m = 0; m < MC; ++m)
                         if (m < p.M) red_add_f32(accum + ((fset * NFA + j) * kMb + m) * 128 + L, acc[j][m]);
                 asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
+                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
                 if (warp == kApplyWarp0 && lane == 0) {
                     const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
                     const int last = (old == contributors - 1) ? 1 : 0;
@@ -810,6 +836,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     ctl->is_last = last;
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
+                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) {
+                    p.trace[blockIdx.x * 48 + 45] = globaltimer_ns();
+                    p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | (ctl->is_last ? 1 : 0) | (contributors << 20));
+                }
                 if (ctl->is_last) {
 #pragma unroll
                     for (int j = 0; j < NFA; ++j) {
@@ -826,6 +856,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     }
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");   // is_last is reused by the next segment
+                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
             }
             if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 5] = globaltimer_ns();
             DPROF_ADD(aw_epi, at);
@@ -963,6 +994,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     constexpr int TN = F::NJ * 128;
     DecodeParams p{};
     p.A = static_cast<const uint16_t*>(a.A);
+    p.Q = static_cast<const uint8_t*>(a.Q);
     p.S = static_cast<const uint16_t*>(a.S);
     p.table2 = static_cast<const uint32_t*>(a.table2);
     p.D = static_cast<uint16_t*>(a.D);
@@ -972,6 +1004,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
     p.G = a.K / a.group_size;
+    p.P = a.N / 16 * BITS;
     p.tile_p = a.tile_p;
     p.gshift = (a.group_size == 64) ? 0 : (a.group_size == 128) ? 1 : 2;
     p.n_tiles = (a.N + TN - 1) / TN;

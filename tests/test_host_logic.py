@@ -170,6 +170,24 @@ def test_op_schema_is_the_references():
     assert callable(flute.qgemm_simple) and callable(flute.qgemm_hadamard)
 
 
+def test_compiled_torch_binding_is_live():
+    """INTEGRATION.md option A, built: TORCH_LIBRARY(flute) + TORCH_LIBRARY_IMPL(flute, CUDA) come from the compiled
+    shim (csrc/torch_binding.cpp, counterpart of flute/csrc/qgemm.cpp:251-260) whenever it has been built."""
+    import os
+    from flute_b200 import ops
+    shim = os.path.join(os.path.dirname(ops.__file__), "_flute_b200_torch.so")
+    if not os.path.exists(shim) or os.environ.get("FLUTE_B200_PY_OPS") == "1":
+        assert ops.BINDING == "python"
+        pytest.skip("compiled binding not built in this tree (build.py --torch)")
+    assert ops.BINDING == "cpp"
+    for name in ("qgemm_raw_simple", "qgemm_raw_simple_hadamard", "hadamard_transform"):
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(f"flute::{name}", "CUDA"), name
+    # the shim links the C-ABI library and nothing CUDA of its own
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", shim], capture_output=True, text=True).stdout
+    assert "libflute_b200.so" in needed
+
+
 def _meta_args(M=(2, 3), N=256, K=128, bits=4, group=64, dtype=torch.float16):
     dev = "meta"
     return (torch.empty(M + (K,), dtype=dtype, device=dev), torch.empty((N // 16 * bits, K), dtype=torch.int16, device=dev),

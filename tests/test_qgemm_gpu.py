@@ -484,6 +484,25 @@ def test_python_api_shapes_and_legacy_names(dev, ws, flute):
         flute.qgemm(x, *args, ws, 4, 96, default_template_id(4), 148)               # unsupported group_size
 
 
+def test_compiled_binding_matches_python_binding(dev, ws, flute):
+    """Both bindings make the same C-ABI call: outputs of torch.ops.flute.* (compiled shim when built) and of the
+    Python implementation agree bit for bit on whole-tile shapes (no split-K reordering), incl. the Hadamard op."""
+    from flute_b200 import ops
+    from flute_b200.templates import default_template_id
+    c = make_case(5, 1024, 512, 4, 64, "float16", seed=23)
+    args = [c[k].to(dev) for k in ("Q", "S", "table", "table2")]
+    x = c["A"].to(dev)
+    tid = default_template_id(4)
+    a = torch.ops.flute.qgemm_raw_simple(x, *args, ws, 4, 64, tid, 148)
+    b = ops._qgemm_cuda(x, *args, ws, 4, 64, tid, 148)
+    assert_close(a, oracle_qgemm(c), c["dtype"], f"binding {ops.BINDING}")
+    assert_close(b, oracle_qgemm(c), c["dtype"], "python binding")
+    ha = torch.ops.flute.qgemm_raw_simple_hadamard(x, *args, ws, 4, 64, 128, tid, 148)
+    hb = ops._qgemm_hadamard_cuda(x, *args, ws, 4, 64, 128, tid, 148)
+    assert_close(ha, hb, c["dtype"], "hadamard op, both bindings")
+    assert torch.equal(torch.ops.flute.hadamard_transform(x, 128), ops.hadamard_transform(x, 128))
+
+
 def test_workspace_reuse_and_flags_restored(dev, flute):
     """One workspace, zeroed once, serves calls of any shape back to back; every counter / accumulator the
     kernel touched is zero again afterwards (contract of flute/utils.py:36-56)."""

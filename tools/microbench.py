@@ -111,6 +111,19 @@ def main():
                         col = t[:, c]; col = col[col > 0] - t0
                         if col.size:
                             print(f"     {nm:10s} {col.min():8d} {int(np.median(col)):8d} {col.max():8d}   (n={col.size})")
+                    if args.trace >= 2 and j == nchain - 1:
+                        # the slowest CTAs of the last launch: where their time goes (last partial segment: reds+bar, atomic, finalize)
+                        tt = trs[j].cpu().numpy()
+                        idx = np.argsort(-tt[:, 6])[:8]
+                        print("     slowest CTAs (ns since launch-0 start): cta start dep-ready mma-first acc-full last-epi | last partial segment: reds-done atom-done fin-done seg-offset contributors last")
+                        live = np.nonzero(tt[:, 0] > 0)[0]
+                        mid = live[np.argsort(tt[live, 6])][len(live) // 2: len(live) // 2 + 3]
+                        for b in list(idx) + [int(x) for x in mid]:
+                            if tt[b, 0] == 0:
+                                continue
+                            r = lambda c: int(tt[b, c] - t0) if tt[b, c] > 0 else -1
+                            f = int(tt[b, 47])
+                            print(f"       {b:4d} {r(0):7d} {r(2):7d} {r(3):7d} {r(4):7d} {r(6):7d} | {r(44):7d} {r(45):7d} {r(46):7d} seg+{(f >> 8) & 0xfff} c={f >> 20} last={f & 1}")
                 if os.environ.get("FLUTE_B200_PROFILE") == "1" and M <= 16 and bits in (2, 4) and (args.variant < 0 or args.variant >= 2):
                     prof = [(8, "producer scale blocks"), (9, "producer wait-empty"), (10, "producer W issue"),
                             (12, "producer iters"), (13, "mma wait-full"), (14, "mma wait-afull"), (15, "mma wait-pempty"),
