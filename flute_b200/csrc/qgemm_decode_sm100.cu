@@ -24,28 +24,23 @@
 //     TMEM accumulator hand-off; one tcgen05.commit per stage signals "smem stage free", "TMEM A slot free" and
 //     "group sums ready" at once.
 //
-// Two footprints of the SAME kernel (template parameter HALF; not a fork):
-//   HALF = false  one CTA per SM: 214 KB shared memory (64 KB LUT at a 256-byte entry stride, 9-stage ring),
-//                 <= 80 registers per thread.
-//   HALF = true   (4-bit, M <= 4) the same 16 dequantiser warps and the same 512 TMEM columns, but at most HALF of
-//                 the SM's shared memory (32 KB LUT in a folded layout, 3-stage ring topped up by an L2 prefetch
-//                 stream, 2 scale slots) and <= 40 registers per thread, grid = #SMs.  Two such CTAs fit on an SM, so
-//                 with programmatic dependent launch the NEXT qgemm's CTA is resident while this one still streams:
-//                 its launch latency, barrier set-up, LUT build, tensor-map fetch, its first weight tiles (static
-//                 weights) and the L2 prefetch of the tiles after those all run under this kernel's stream instead
-//                 of costing ~7 us per launch.  Tensor memory is the one thing two CTAs
-//                 cannot share: the newcomer's tcgen05.alloc simply blocks until this CTA frees its columns at exit
-//                 (only the TMEM users -- dequantisers, MMA issuers, apply warps -- wait for it; the producer, the
-//                 activation and the scale warps do not).
+// One CTA per SM (214 KB shared memory, 512 TMEM columns).  A half-SM footprint of this kernel (two CTAs of
+// CONSECUTIVE launches co-resident under programmatic dependent launch, 32 KB folded LUT, 3-stage ring, 40 registers)
+// was built and measured in round 2 and removed again: co-residency works, but 113 KB leaves a 3-stage ring, the
+// running CTA then has ~1.5 weight tiles in flight and streams at 1.6 TB/s instead of 3.2 (gpurun r02a/r02b,
+// DESIGN.md section 3.1).  What a launch can hide behind its predecessor is done inside this footprint instead:
+// weights, scales and the LUT never wait for the previous kernel (static weights), the dequantisers fill all three
+// TMEM A slots before the activations exist, and the split-K fix-up runs in its own warp off the streaming path.
 //
 // Warp roles (persistent over a contiguous Stream-K range of (tile, k) stages).  DQ = dequantiser warps
-// (16); 800 threads for M <= 4 (HALF: 768), 896 for the opt-in 5 <= M <= 16 variant:
+// (16); 832 threads for M <= 4, 928 for the opt-in 5 <= M <= 16 variant:
 //   warps 0..DQ-1    dequantisers: warp w owns TMEM lane quarter w%4 and a fixed set of 16-byte quads of its row
 //   warp DQ          TMA producer (packed weights, one 128-row x 64-k box per stage; optional L2 prefetch ahead)
 //   warps DQ+1,DQ+3  tcgen05.mma issuers (alternate scale groups; warp DQ+1 also allocates TMEM)
 //   warp DQ+2        activation rows of every stage (16-byte cp.async, up to three stages ahead)
 //   warps DQ+4..     4 (8 for M > 4) scale application (acc += S * P_g), epilogue and split-K fix-up
-//   last warp        scale blocks (cp.async); for M > 4 and for HALF the activation warp does this
+//   next warp        split-K fix-up: arrival counter, last-arriver conversion of the fp32 partial sums to D
+//   last warp        scale blocks (cp.async); for M > 4 the activation warp does this
 #include "ptx.cuh"
 #include "qgemm_sm100.h"
 
@@ -71,35 +66,28 @@ namespace dec {
 // CK2     k-pairs per TMEM chunk (an A slot = NJ*CK2 columns);  CPS chunks per 64-k stage
 // DQ      dequantiser warps;  DQG sets of them that convert alternate stages
 // LUTB    bytes of the lane-replicated pair LUT
-template <int BITS, bool HALF>
+template <int BITS>
 struct DCfg;
 template <>
-struct DCfg<4, false> {
+struct DCfg<4> {
     static constexpr int NJ = 4, CK2 = 32, CPS = 1, LUTN = 256, A_SLOTS = 3, P_SLOTS = 2;
     static constexpr int DQ = 16, DQG = 2, SC_SLOTS = 3, MAX_STAGES = 10, TMEM_COLS = 512, LUTB = 256 * 256;
-    static constexpr uint32_t SMEM_BUDGET = 232448u;
 };
 template <>
-struct DCfg<4, true> {
-    static constexpr int NJ = 4, CK2 = 32, CPS = 1, LUTN = 256, A_SLOTS = 3, P_SLOTS = 2;
-    static constexpr int DQ = 16, DQG = 2, SC_SLOTS = 2, MAX_STAGES = 4, TMEM_COLS = 512, LUTB = 256 * 128;
-    static constexpr uint32_t SMEM_BUDGET = 115712u;      // (228 KB - 2 x 1 KB reserved) / 2: two CTAs per SM
-};
-template <>
-struct DCfg<2, false> {
+struct DCfg<2> {
     static constexpr int NJ = 8, CK2 = 16, CPS = 2, LUTN = 16, A_SLOTS = 2, P_SLOTS = 2;
     static constexpr int DQ = 16, DQG = 1, SC_SLOTS = 3, MAX_STAGES = 10, TMEM_COLS = 512, LUTB = 16 * 256;
-    static constexpr uint32_t SMEM_BUDGET = 232448u;
 };
 
 // apply warps: 4 (each all NJ fields) for M <= 4; 8 (two field halves) when a field needs 16 accumulators
 __host__ __device__ constexpr int apply_warps(int mc) { return mc > 4 ? 8 : 4; }
-// full footprint, M <= 4: one more warp copies the scale blocks; otherwise the activation warp does (HALF: 24 warps,
-// so that two CTAs x 768 threads get 40 registers each -- a 25th warp rounds the allocation down to 32)
-__host__ __device__ constexpr bool has_scale_warp(int mc, bool half) { return mc <= 4 && !half; }
-__host__ __device__ constexpr int threads_for(int dq, int mc, bool half) {
-    return (dq + 4 + apply_warps(mc) + (has_scale_warp(mc, half) ? 1 : 0)) * 32;
+// M <= 4: one more warp copies the scale blocks; with 8 apply warps the activation warp does
+__host__ __device__ constexpr bool has_scale_warp(int mc) { return mc <= 4; }
+// dequantisers + producer, 2 MMA issuers, activation warp + apply warps + fix-up warp (+ scale warp)
+__host__ __device__ constexpr int threads_for(int dq, int mc) {
+    return (dq + 4 + apply_warps(mc) + 1 + (has_scale_warp(mc) ? 1 : 0)) * 32;
 }
+constexpr uint32_t kSmemBudget = 232448u;
 constexpr int kMaxStagesAny = 10;
 constexpr int kMaxScSlots = 3;
 constexpr int kWBytes = 128 * 128;   // packed-weight part of a stage: 128 rows x 64 k x 2 B
@@ -118,8 +106,8 @@ struct Ctl {
     uint64_t sc_full[kMaxScSlots];
     uint64_t sc_empty[kMaxScSlots];
     uint64_t tmem_ready;     // the allocating warp arrives once the TMEM base address is in tmem_base
+    uint64_t fix_full[2];    // partial-tile hand-over apply warps -> fix-up warp (a contiguous range has <= 2 partial segments)
     uint32_t tmem_base;
-    int is_last;
 };
 
 struct DecodeParams {
@@ -210,19 +198,6 @@ __device__ __forceinline__ uint32_t code_lane(uint32_t w, uint32_t lane4) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(lane4), "n"(0x6504 + (J << 4)));
     return r;
 }
-// Folded 32 KB LUT (HALF): entry e of lane l sits at (e & 127) * 256 + (e >> 7) * 128 + l * 4, so the offset is
-// still ONE prmt per code -- byte 1 = code & 0x7f (from w7 = w & 0x7f7f7f7f), byte 0 = (code & 0x80) | lane*4 (from
-// x = (w & 0x80808080) | lane4 replicated), bytes 2..3 = sign-replicated byte of w7 = 0 -- plus two LOP3 per WORD of
-// four codes (2.5 instead of 2 issue slots per pair; a shift of the 256-stride offset would cost 3).
-template <int J>
-__device__ __forceinline__ uint32_t code_lane_folded(uint32_t w7, uint32_t x) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w7), "r"(x), "n"(((8 | J) << 12) | ((8 | J) << 8) | (J << 4) | (4 + J)));
-    return r;
-}
-__host__ __device__ constexpr uint32_t lut_entry_offset(int e, bool folded) {
-    return folded ? (uint32_t)((e & 127) * 256 + (e >> 7) * 128) : (uint32_t)(e * 256);
-}
 __device__ __forceinline__ void tmem_st_x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
                  : "memory");
@@ -287,7 +262,7 @@ struct Piece;
 template <>
 struct Piece<4> {
     // two 16-byte quads (8 consecutive k-pairs) of row L -> 4 fields x 8 TMEM columns, field blocks FSTRIDE columns apart
-    template <bool FOLDED, int FSTRIDE>
+    template <int FSTRIDE>
     static __device__ __forceinline__ void run(uint32_t row, int pq0, int pq1, uint32_t lut, uint32_t lane4, uint32_t tcol) {
         const uint4 v0 = lds128(row + (uint32_t)(pq0 << 4));
         const uint4 v1 = lds128(row + (uint32_t)(pq1 << 4));
@@ -295,44 +270,13 @@ struct Piece<4> {
         uint32_t r[4][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if constexpr (FOLDED) {
-                const uint32_t w7 = w[i] & 0x7f7f7f7fu;
-                uint32_t x;      // (w & 0x80808080) | lane4 (lane*4 replicated into every byte)
-                asm("lop3.b32 %0, %1, 0x80808080, %2, 0xEA;" : "=r"(x) : "r"(w[i]), "r"(lane4));
-                r[0][i] = lds32(lut + code_lane_folded<0>(w7, x));
-                r[1][i] = lds32(lut + code_lane_folded<1>(w7, x));
-                r[2][i] = lds32(lut + code_lane_folded<2>(w7, x));
-                r[3][i] = lds32(lut + code_lane_folded<3>(w7, x));
-            } else {
-                r[0][i] = lds32(lut + code_lane<0>(w[i], lane4));
-                r[1][i] = lds32(lut + code_lane<1>(w[i], lane4));
-                r[2][i] = lds32(lut + code_lane<2>(w[i], lane4));
-                r[3][i] = lds32(lut + code_lane<3>(w[i], lane4));
-            }
+            r[0][i] = lds32(lut + code_lane<0>(w[i], lane4));
+            r[1][i] = lds32(lut + code_lane<1>(w[i], lane4));
+            r[2][i] = lds32(lut + code_lane<2>(w[i], lane4));
+            r[3][i] = lds32(lut + code_lane<3>(w[i], lane4));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * FSTRIDE, r[j]);
-    }
-};
-// Register-lean form for the co-resident footprint (<= 40 registers per thread): ONE 16-byte quad (4 k-pairs) of row L
-// -> 4 fields x 4 TMEM columns, through the folded LUT.  `w` was loaded by the caller one call ahead.
-struct Piece4Lean {
-    template <int FSTRIDE>
-    static __device__ __forceinline__ void run(const uint4& v, uint32_t lut, uint32_t lane4rep, uint32_t tcol) {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t r[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t w7 = w[i] & 0x7f7f7f7fu;
-            uint32_t x;      // (w & 0x80808080) | lane*4 in every byte
-            asm("lop3.b32 %0, %1, 0x80808080, %2, 0xEA;" : "=r"(x) : "r"(w[i]), "r"(lane4rep));
-            r[0][i] = lds32(lut + code_lane_folded<0>(w7, x));
-            r[1][i] = lds32(lut + code_lane_folded<1>(w7, x));
-            r[2][i] = lds32(lut + code_lane_folded<2>(w7, x));
-            r[3][i] = lds32(lut + code_lane_folded<3>(w7, x));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tmem_st_x4(tcol + j * FSTRIDE, r[j][0], r[j][1], r[j][2], r[j][3]);
     }
 };
 template <>
@@ -365,10 +309,10 @@ __device__ __forceinline__ float scale_to_f32(uint32_t s16) {
     else return __half2float(__ushort_as_half((unsigned short)s16));
 }
 
-template <int BITS, bool BF16, int MC, bool HALF>
-__global__ void __launch_bounds__(threads_for(DCfg<BITS, HALF>::DQ, MC, HALF), HALF ? 2 : 1)
+template <int BITS, bool BF16, int MC>
+__global__ void __launch_bounds__(threads_for(DCfg<BITS>::DQ, MC), 1)
 qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodeParams p) {
-    using F = DCfg<BITS, HALF>;
+    using F = DCfg<BITS>;
     constexpr int NJ = F::NJ, CK2 = F::CK2, CPS = F::CPS;
     constexpr int AS = F::A_SLOTS, PS = F::P_SLOTS;
     constexpr int kDqWarps = F::DQ;
@@ -384,11 +328,11 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     constexpr uint32_t kPCol0 = AS * kACols;       // P slots sit after the A slots
     constexpr uint32_t kPCols = NJ * kMb;
     constexpr int kApplyWarps = apply_warps(MC);
-    constexpr bool kScaleWarpExists = has_scale_warp(MC, HALF);
-    constexpr int kScaleWarp = kApplyWarp0 + kApplyWarps;   // exists iff kScaleWarpExists
+    constexpr bool kScaleWarpExists = has_scale_warp(MC);
+    constexpr int kFixWarp = kApplyWarp0 + kApplyWarps;     // split-K fix-up, off the streaming path
+    constexpr int kScaleWarp = kFixWarp + 1;                // exists iff kScaleWarpExists
     constexpr int NFA = NJ / (kApplyWarps / 4);   // fields per apply warp
     static_assert(kPCol0 + PS * kPCols <= (uint32_t)F::TMEM_COLS, "TMEM budget");
-    static_assert(!HALF || (BITS == 4 && MC <= 4), "half-SM footprint: 4-bit, M <= 4");
     static_assert((kApplyWarp0 & 3) == 0, "apply warp w must own TMEM lane quarter w & 3");
 
     extern __shared__ uint8_t smem_raw[];
@@ -447,12 +391,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             mbar_init(smem_u32(&ctl->sc_empty[s]), kApplyWarps);
         }
         mbar_init(smem_u32(&ctl->tmem_ready), 1);
+        for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&ctl->fix_full[s]), kApplyWarps);
         mbar_fence_init();
     }
     // First sync: barriers visible.  The producer starts streaming right after it, the dequant warps build the LUT;
     // tensor memory is allocated AFTER it by one warp, and only the TMEM users wait for the address (tmem_ready):
-    // when the previous launch's CTA still holds this SM's columns (HALF, co-resident under PDL) the allocation
-    // blocks until that CTA exits, and everything that does not touch TMEM proceeds meanwhile.
+    // should another kernel's CTA still hold this SM's columns the allocation blocks until it exits, and everything
+    // that does not touch TMEM proceeds meanwhile.
     __syncthreads();
     pdl_launch_dependents();
     if (warp == kMmaWarp) {
@@ -509,8 +454,8 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         // =============================== TMA producer ===============================
         // Packed weights by TMA, one 128-row x 64-k box per stage.  Static data: nothing here waits for the previous
         // kernel.  With l2_prefetch = PF > 0 the boxes of the next PF stages beyond the ring are pulled into L2 first
-        // (no shared-memory destination), so that a short ring (HALF: 3 stages) still keeps enough bytes in flight
-        // towards HBM, and a CTA that is resident early (PDL) warms L2 with its first 3 + PF stages while it waits.
+        // (no shared-memory destination); off by default (no gain with a 9-stage ring, gpurun r02a), kept as a tuning
+        // knob for short rings (force_stages).
         if (rg.it1 > rg.it0) {
             const uint64_t pol_w = policy_evict_first();
             const int n_it = rg.it1 - rg.it0;
@@ -708,6 +653,65 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
             }
         }
+    } else if (warp == kFixWarp) {
+        // =============================== split-K fix-up ==============================
+        // For every partial segment of this CTA's range, in order: once the apply warps have issued their reductions,
+        // bump the tile's arrival counter (release: their red.adds happen-before it through the mbarrier hand-over);
+        // the CTA that arrives last reads the completed fp32 sums back, zeroes the scratch (workspace contract:
+        // zero between launches) and writes the tile in T.  A contiguous Stream-K range has at most two partial
+        // segments (its first and its last tile), one mbarrier each.
+        if (rg.it1 > rg.it0) {
+            int n_fix = 0;
+            bool synced = false;
+            for (int it = rg.it0; it < rg.it1;) {
+                const int tile = it / p.k_iters;
+                const int kb = it - tile * p.k_iters;
+                const int ke = min(p.k_iters, kb + (rg.it1 - it));
+                if (!((kb == 0) && (ke == p.k_iters))) {
+                    wait(smem_u32(&ctl->fix_full[n_fix]), 0u, p, DSITE_PFULL, 2);
+                    ++n_fix;
+                    if (!synced) { pdl_wait_prior_grids(); synced = true; }
+                    if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
+                    const int tile_it0 = tile * p.k_iters;
+                    const int first_cta = cta_of(total, tile_it0, grid);
+                    const int contributors = cta_of(total, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
+                    int last = 0;
+                    if (lane == 0) {
+                        const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
+                        last = (old == contributors - 1) ? 1 : 0;
+                        if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
+                    }
+                    last = __shfl_sync(0xffffffffu, last, 0);
+                    if (p.trace != nullptr && lane == 0) {
+                        p.trace[blockIdx.x * 48 + 45] = globaltimer_ns();
+                        p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | last | (contributors << 20));
+                    }
+                    if (last) {
+                        __threadfence();      // every lane: order its reads after lane 0's acquire
+                        float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
+                        const int n_base = tile * TN;
+#pragma unroll 1
+                        for (int m = 0; m < p.M; ++m) {
+                            float v[NJ][4];
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) v[j][qq] = __ldcg(accum + (j * kMb + m) * 128 + qq * 32 + lane);
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) {
+                                    accum[(j * kMb + m) * 128 + qq * 32 + lane] = 0.f;
+                                    const int n = n_base + n_local<BITS, NJ>(qq * 32 + lane, j, p.tile_p);
+                                    if (n < p.N) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(v[j][qq]);
+                                }
+                        }
+                    }
+                    if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
+                }
+                it += ke - kb;
+            }
+        }
     } else if (warp >= kApplyWarp0) {
         // ===================== scale + accumulate + epilogue ========================
         const int q = warp & 3;
@@ -725,6 +729,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         int sc_idx = 0;
         uint32_t sc_par = 0;
         bool synced = false;
+        int n_fix = 0;                     // partial segments handed to the fix-up warp so far (<= 2)
         DPROF_DECL(aw_pfull = 0, aw_sc = 0, aw_work = 0, aw_epi = 0);
         DPROF_T0(at);
         for (int it = rg.it0; it < rg.it1;) {
@@ -816,47 +821,18 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     }
                 }
             } else {
-                // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left
-                // zero on exit); the CTA that arrives last converts and writes the tile.
-                const int tile_it0 = tile * p.k_iters;
-                const int first_cta = cta_of(total, tile_it0, grid);
-                const int contributors = cta_of(total, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
+                // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left zero
+                // on exit), then hand over to the fix-up warp (arrival counter, last-arriver conversion) and carry on
+                // with the next segment: nothing on the streaming path waits for a global-memory round trip.
                 float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
 #pragma unroll
                 for (int j = 0; j < NFA; ++j)
 #pragma unroll
                     for (int m = 0; m < MC; ++m)
                         if (m < p.M) red_add_f32(accum + ((fset * NFA + j) * kMb + m) * 128 + L, acc[j][m]);
-                asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
-                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
-                if (warp == kApplyWarp0 && lane == 0) {
-                    const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
-                    const int last = (old == contributors - 1) ? 1 : 0;
-                    if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
-                    ctl->is_last = last;
-                }
-                asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
-                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) {
-                    p.trace[blockIdx.x * 48 + 45] = globaltimer_ns();
-                    p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | (ctl->is_last ? 1 : 0) | (contributors << 20));
-                }
-                if (ctl->is_last) {
-#pragma unroll
-                    for (int j = 0; j < NFA; ++j) {
-                        const int n = n_base + nloc[j];
-#pragma unroll
-                        for (int m = 0; m < MC; ++m) {
-                            if (m < p.M) {
-                                float* src = accum + ((fset * NFA + j) * kMb + m) * 128 + L;
-                                const float v = __ldcg(src);
-                                *src = 0.f;
-                                if (n < p.N) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(v);
-                            }
-                        }
-                    }
-                }
-                asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");   // is_last is reused by the next segment
-                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->fix_full[n_fix]));
+                ++n_fix;
             }
             if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 5] = globaltimer_ns();
             DPROF_ADD(aw_epi, at);
@@ -880,14 +856,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 #pragma unroll
             for (int i = 0; i < kEntriesPerWarp; ++i) {
                 const uint32_t vi = __shfl_sync(0xffffffffu, v, i);
-                if (e0 + i < F::LUTN) sts32(lut + lut_entry_offset(e0 + i, HALF) + lane * 4, vi);
+                if (e0 + i < F::LUTN) sts32(lut + (uint32_t)(e0 + i) * 256u + lane * 4, vi);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
         }
         if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 1] = globaltimer_ns();
         const uint32_t tmem = (rg.it1 > rg.it0) ? tmem_base_when_ready() : 0u;
-        // HALF: lane*4 replicated into every byte (operand of code_lane_folded); else lane*4
-        const uint32_t lane4 = HALF ? (uint32_t)lane * 0x04040404u : (uint32_t)lane * 4;
+        const uint32_t lane4 = (uint32_t)lane * 4;
 
         const uint32_t wrow = (uint32_t)L * 128;
         const int xq = L & 7;
@@ -936,20 +911,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 tc_fence_after();
                 const uint32_t tcol = tmem + lane_sel + aslot * kACols;
                 if (do_dq) {
-                    if constexpr (BITS == 4 && !HALF) {
+                    if constexpr (BITS == 4) {
                         // this warp's 16 k-pairs of the stage: 16-byte quads 4*hw .. 4*hw + 3 of row L
-                        Piece<4>::run<false, CK2>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
-                        Piece<4>::run<false, CK2>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
-                    } else if constexpr (BITS == 4) {
-                        // same 4 quads, 16 look-ups at a time (<= 40 registers), each quad's words loaded one call ahead
-                        uint4 va = lds128(row + (uint32_t)(((4 * hw) ^ xq) << 4));
-                        uint4 vb = lds128(row + (uint32_t)(((4 * hw + 1) ^ xq) << 4));
-                        Piece4Lean::run<CK2>(va, lut, lane4, tcol + hw * 16);
-                        va = lds128(row + (uint32_t)(((4 * hw + 2) ^ xq) << 4));
-                        Piece4Lean::run<CK2>(vb, lut, lane4, tcol + hw * 16 + 4);
-                        vb = lds128(row + (uint32_t)(((4 * hw + 3) ^ xq) << 4));
-                        Piece4Lean::run<CK2>(va, lut, lane4, tcol + hw * 16 + 8);
-                        Piece4Lean::run<CK2>(vb, lut, lane4, tcol + hw * 16 + 12);
+                        Piece<4>::run<CK2>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
+                        Piece<4>::run<CK2>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
                     } else {
                         // half stage c: quad c*4 + sw
                         Piece<2>::run(row, (c * 4 + hw) ^ xq, lut, lane4, tcol + hw * 4);
@@ -988,9 +953,9 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     }
 }
 
-template <int BITS, bool BF16, int MC, bool HALF>
+template <int BITS, bool BF16, int MC>
 static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
-    using F = DCfg<BITS, HALF>;
+    using F = DCfg<BITS>;
     constexpr int TN = F::NJ * 128;
     DecodeParams p{};
     p.A = static_cast<const uint16_t*>(a.A);
@@ -1012,10 +977,10 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
     p.ablate = a.ablate;
     p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
-    p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : (HALF ? 6 : 0);
+    p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : 0;
 
     const uint32_t fixed = F::SC_SLOTS * TN * 16 + F::LUTB + sizeof(Ctl) + 1024 /*alignment slack*/;
-    int stages = (int)((F::SMEM_BUDGET - fixed) / kStageBytes);
+    int stages = (int)((kSmemBudget - fixed) / kStageBytes);
     if (stages > F::MAX_STAGES) stages = F::MAX_STAGES;
     if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
     if (stages < 2) return FB_ERR_INTERNAL;
@@ -1024,7 +989,6 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
     const long long total = (long long)p.n_tiles * p.k_iters;
     if (total > 0x3fffffffLL) return FB_ERR_SHAPE;
-    // HALF: still ONE CTA per SM of this launch -- the other half of each SM is for the next launch's CTAs (PDL).
     int grid = a.num_sms;
     if (a.force_grid > 0) grid = a.force_grid;
     if (grid > total) grid = (int)total;
@@ -1039,19 +1003,18 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, 64, 128,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
-    auto kern = qgemm_decode_kernel<BITS, BF16, MC, HALF>;
+    auto kern = qgemm_decode_kernel<BITS, BF16, MC>;
     static PerDeviceOnce attr_set;      // one per template instantiation
     if (!attr_set.done(a.device)) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM_BUDGET) != cudaSuccess) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess) {
             cudaGetLastError();
             return FB_ERR_LAUNCH;
         }
-        if (HALF) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set.mark(a.device);
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads_for(F::DQ, MC, HALF));
+    cfg.blockDim = dim3(threads_for(F::DQ, MC));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[1];
@@ -1072,16 +1035,10 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 }
 
 template <int BITS, bool BF16>
-static int launch_mc(const QgemmArgs& a, cudaStream_t stream, bool half) {
-    if constexpr (BITS == 4) {
-        if (half && a.M <= 4) {
-            if (a.M == 1) return launch_t<4, BF16, 1, true>(a, stream);
-            return launch_t<4, BF16, 4, true>(a, stream);
-        }
-    }
-    if (a.M == 1) return launch_t<BITS, BF16, 1, false>(a, stream);
-    if (a.M <= 4) return launch_t<BITS, BF16, 4, false>(a, stream);
-    if constexpr (BITS == 4) return launch_t<BITS, BF16, 16, false>(a, stream);
+static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
+    if (a.M == 1) return launch_t<BITS, BF16, 1>(a, stream);
+    if (a.M <= 4) return launch_t<BITS, BF16, 4>(a, stream);
+    if constexpr (BITS == 4) return launch_t<BITS, BF16, 16>(a, stream);
     return FB_ERR_INTERNAL;
 }
 
@@ -1097,18 +1054,9 @@ bool qgemm_decode_supported(const QgemmArgs& a) {
     return (a.num_bits == 4 || a.num_bits == 2) && a.M <= m_max;
 }
 
-// Footprint: variant 3 = half-SM, variant 4 = full-SM, otherwise the engine's choice.
-bool qgemm_decode_half_footprint(const QgemmArgs& a) {
-    if (a.num_bits != 4 || a.M > 4) return false;
-    if (a.variant == 3) return true;
-    if (a.variant == 4) return false;
-    return false;
-}
-
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream) {
-    const bool half = qgemm_decode_half_footprint(a);
-    if (a.num_bits == 4) return a.bf16 ? dec::launch_mc<4, true>(a, stream, half) : dec::launch_mc<4, false>(a, stream, half);
-    if (a.num_bits == 2) return a.bf16 ? dec::launch_mc<2, true>(a, stream, false) : dec::launch_mc<2, false>(a, stream, false);
+    if (a.num_bits == 4) return a.bf16 ? dec::launch_mc<4, true>(a, stream) : dec::launch_mc<4, false>(a, stream);
+    if (a.num_bits == 2) return a.bf16 ? dec::launch_mc<2, true>(a, stream) : dec::launch_mc<2, false>(a, stream);
     return FB_ERR_BITS;
 }
 

@@ -39,8 +39,7 @@ struct QgemmArgs {
     int force_grid;
     int force_streamk;
     int ablate;    // perf ablation bits (tests only): 1 skip MMA issue, 2 skip dequant math
-    int variant;   // -1 auto; general kernel: 0 LARGE (1 CTA/SM), 1 SMALL (2 CTAs/SM); decode kernel: 2 also 5 <= M <= 16,
-                   // 3 half-SM footprint, 4 full-SM footprint
+    int variant;   // -1 auto; general kernel: 0 LARGE (1 CTA/SM), 1 SMALL (2 CTAs/SM); decode kernel: 2 also 5 <= M <= 16
     int l2_prefetch;   // decode kernel: L2 prefetch distance in stages, -1 = engine's choice
 };
 
@@ -80,7 +79,6 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream);
 // decode-shaped kernel (M <= 16, 2/4-bit): qgemm_decode_sm100.cu
 bool qgemm_decode_supported(const QgemmArgs& a);
 int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream);
-bool qgemm_decode_half_footprint(const QgemmArgs& a);
 // prefill-shaped kernel (M > 16, 4-bit): qgemm_prefill_sm100.cu
 // The tail of the workspace holds its per-CTA partial-tile slots (2 x 128 KB per SM, contents undefined between
 // launches); the zero-invariant fp32 accumulators of the other kernels must stay below it.

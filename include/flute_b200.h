@@ -134,7 +134,8 @@ FLUTE_B200_API void flute_b200_set_trace_buffer(void* device_ptr);
 /* Test hook: kernel selection for later qgemm launches: -1 automatic (default: decode kernel for M <= 4 at 2/4 bits,
  * prefill kernel for M > 16 at 4 bits, general kernel otherwise); 0 general kernel, LARGE footprint (1 CTA/SM);
  * 1 general kernel, SMALL footprint (2 CTAs/SM; M <= 16, 2/4 bits); 2 automatic, but the decode kernel also takes
- * 5 <= M <= 16 at 4 bits; 3 EXPERIMENTAL half-SM decode kernel (4 bits, M <= 4; not validated on hardware yet). */
+ * 5 <= M <= 16 at 4 bits.  Bits 8..15: perf-ablation mask, bits 16..23: decode kernel's L2 prefetch distance + 1
+ * (tools/microbench.py only). */
 FLUTE_B200_API void flute_b200_set_variant(int variant);
 
 /* Test hook: like flute_b200_qgemm with explicit tiling overrides (0 / -1 = engine's choice) and an
