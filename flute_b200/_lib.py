@@ -30,6 +30,7 @@ EXPORTS = (
     "flute_b200_qgemm_debug",
     "flute_b200_set_trace_buffer",
     "flute_b200_set_variant",
+    "flute_b200_dispatch_name",
 )
 
 F16, BF16 = 0, 1
@@ -75,6 +76,8 @@ def _load() -> ctypes.CDLL:
     lib.flute_b200_set_variant.restype = None
     lib.flute_b200_set_trace_buffer.argtypes = [_vp]
     lib.flute_b200_set_trace_buffer.restype = None
+    lib.flute_b200_dispatch_name.argtypes = [_i, _i, _i]
+    lib.flute_b200_dispatch_name.restype = ctypes.c_char_p
     lib.flute_b200_check.argtypes = [_i]
     lib.flute_b200_check.restype = _i
     return lib
@@ -83,6 +86,11 @@ def _load() -> ctypes.CDLL:
 lib = _load()
 if os.environ.get("FLUTE_B200_VARIANT"):          # tools / A-B runs only: pin a kernel variant for the whole process
     lib.flute_b200_set_variant(int(os.environ["FLUTE_B200_VARIANT"], 0))
+
+
+def dispatch_name(M: int, N: int, K: int, num_bits: int, group_size: int, dtype_code: int) -> str:
+    """The kernel flute_b200_qgemm dispatches to for this problem (automatic selection)."""
+    return lib.flute_b200_dispatch_name(M, num_bits, dtype_code).decode()
 
 
 def check(rc: int) -> None:

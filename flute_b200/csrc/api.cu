@@ -37,6 +37,7 @@ std::mutex g_dev_mutex;                    // guards the lazy per-device initial
 long g_timeout_ms = 10000;
 unsigned long long* g_trace = nullptr;
 int g_ablate = 0;
+int g_grid_slack = 0;                     // test hook: SMs left idle per launch (grid = num_sms - slack)
 int g_l2_prefetch = -1;                   // test hook: decode kernel's L2 prefetch distance (-1 = engine's choice)
 int g_variant = -1;                       // test hook: kernel footprint override   // test hook: per-CTA globaltimer stamps
 
@@ -142,6 +143,7 @@ int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* 
     a.l2_prefetch = g_l2_prefetch;
     a.timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
     a.force_mb = force_mb; a.force_stages = force_stages; a.force_grid = force_grid; a.force_streamk = force_streamk;
+    if (a.force_grid <= 0 && g_grid_slack > 0 && g_grid_slack < a.num_sms) a.force_grid = a.num_sms - g_grid_slack;
     rc = fb::qgemm_launch(a, static_cast<cudaStream_t>(stream));
     switch (rc) {
         case FB_OK: return FB_OK;
@@ -253,6 +255,11 @@ int flute_b200_max_batch_tile(int num_bits) {
     return fb::qgemm_max_mb(num_bits);
 }
 
+const char* flute_b200_dispatch_name(int M, int num_bits, int dtype) {
+    if (num_bits != 2 && num_bits != 3 && num_bits != 4) return "unsupported";
+    return fb::qgemm_dispatch_name(M, num_bits, dtype == FLUTE_B200_BF16);
+}
+
 const char* flute_b200_last_error(void) { return g_last_error; }
 
 const char* flute_b200_error_string(int code) {
@@ -281,11 +288,12 @@ int flute_b200_version(void) { return FLUTE_B200_VERSION; }
 void flute_b200_set_timeout_ms(long ms) { g_timeout_ms = ms; }
 
 void flute_b200_set_variant(int variant) {
-    if (variant < 0) { g_variant = -1; g_ablate = 0; g_l2_prefetch = -1; return; }
+    if (variant < 0) { g_variant = -1; g_ablate = 0; g_l2_prefetch = -1; g_grid_slack = 0; return; }
     g_variant = variant & 0xff;
     if (g_variant == 0xff) g_variant = -1;
     g_ablate = (variant >> 8) & 0xff;   // undocumented perf-ablation bits, tools/microbench.py only
     g_l2_prefetch = ((variant >> 16) & 0xff) - 1;   // tools only: 0 = engine's choice, n + 1 = prefetch n stages
+    g_grid_slack = (variant >> 24) & 0x7f;          // tools only: SMs left idle per launch
 }
 
 void flute_b200_set_trace_buffer(void* device_ptr) { g_trace = static_cast<unsigned long long*>(device_ptr); }

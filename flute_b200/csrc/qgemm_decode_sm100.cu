@@ -131,6 +131,18 @@ struct DecodeParams {
     int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
     int l2_prefetch;     // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
     uint32_t partial_offset;
+    // Tensor-parallel column shard with the exchange fused in (tp > 1): the tile writer stores its [M, tile] slice into
+    // EVERY rank's gathered buffer (peer-mapped pointers, NVLink) at column offset rank * N, then bumps that buffer's
+    // arrival counter on every rank (release, system scope); the activation warp of the consuming launch waits on its
+    // own rank's counter of the buffer A lives in (acquire) -- no collective kernel, no host involvement.
+    int tp, rank;
+    int n_total;                  // row stride of the gathered output (= tp * N)
+    uint16_t* out_peers[8];
+    unsigned* flag_peers[8];
+    const unsigned* in_flag;      // arrival counter guarding A on this rank (nullptr: A is local / complete)
+    unsigned in_per_step;         // arrivals on in_flag per step; expected = (epoch - 1) * in_per_step + in_offset
+    unsigned in_offset;
+    const unsigned* epoch;        // device word: step number (>= 1)
 };
 
 enum : int { DSITE_FULL = 21, DSITE_AEMPTY, DSITE_PFULL, DSITE_SCFULL, DSITE_EMPTY, DSITE_SCEMPTY, DSITE_AFULL, DSITE_PEMPTY };
@@ -228,6 +240,14 @@ __device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
     return old;
 }
+__device__ __forceinline__ void red_release_sys_add_u32(unsigned* addr, unsigned v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* addr) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
+}
 // Pull one packed-weight box into L2 without a shared-memory destination.
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
@@ -279,6 +299,21 @@ struct Piece<4> {
         for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * FSTRIDE, r[j]);
     }
 };
+// The same 32 look-ups on words the caller already holds (software-pipelined dequantiser loop).
+template <int FSTRIDE>
+__device__ __forceinline__ void piece4_from_regs(const uint4& v0, const uint4& v1, uint32_t lut, uint32_t lane4, uint32_t tcol) {
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t r[4][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r[0][i] = lds32(lut + code_lane<0>(w[i], lane4));
+        r[1][i] = lds32(lut + code_lane<1>(w[i], lane4));
+        r[2][i] = lds32(lut + code_lane<2>(w[i], lane4));
+        r[3][i] = lds32(lut + code_lane<3>(w[i], lane4));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * FSTRIDE, r[j]);
+}
 template <>
 struct Piece<2> {
     static __device__ __forceinline__ void run(uint32_t row, int pq, uint32_t lut, uint32_t lane4, uint32_t tcol) {
@@ -411,6 +446,22 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         wait(smem_u32(&ctl->tmem_ready), 0u, p, DSITE_AFULL, -1);
         tc_fence_after();
         return *reinterpret_cast<volatile uint32_t*>(&ctl->tmem_base);
+    };
+
+    // D[m, n] = v -- locally, or (tensor parallel) into every rank's gathered buffer at this rank's column offset
+    auto store_out = [&](int m, int n, uint16_t v) {
+        if (p.tp <= 1) {
+            p.D[(size_t)m * p.N + n] = v;
+        } else {
+            const size_t off = (size_t)m * p.n_total + (size_t)p.rank * p.N + n;
+#pragma unroll 1
+            for (int r = 0; r < p.tp; ++r) p.out_peers[r][off] = v;
+        }
+    };
+    // after a tile's stores (made visible system-wide by the callers' fences): one arrival on every rank's counter
+    auto signal_tile = [&]() {
+#pragma unroll 1
+        for (int r = 0; r < p.tp; ++r) red_release_sys_add_u32(p.flag_peers[r], 1u);
     };
 
     // One step of the scale-block schedule (called once per stage, in stage order, by ONE warp): when stage (tile, k)
@@ -602,6 +653,22 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             // the wait for the previous kernel.
             if (!kScaleWarpExists && p.static_weights) scale_step(tile, k, nb, last_blk);
             if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
+            if (p.in_flag != nullptr) {
+                // tensor parallel: A is a gathered buffer; every rank's slice must have arrived (acquire, system scope)
+                if (lane == 0) {
+                    const unsigned expected = (ld_acquire_sys_u32(p.epoch) - 1u) * p.in_per_step + p.in_offset;
+                    uint64_t t0 = 0;
+                    uint32_t spins = 0;
+                    while ((int)(ld_acquire_sys_u32(p.in_flag) - expected) < 0) {
+                        if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
+                            const uint64_t now = globaltimer_ns();
+                            if (t0 == 0) t0 = now;
+                            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, 0u, expected, -2);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
             if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
@@ -703,8 +770,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                                 for (int qq = 0; qq < 4; ++qq) {
                                     accum[(j * kMb + m) * 128 + qq * 32 + lane] = 0.f;
                                     const int n = n_base + n_local<BITS, NJ>(qq * 32 + lane, j, p.tile_p);
-                                    if (n < p.N) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(v[j][qq]);
+                                    if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]));
                                 }
+                        }
+                        if (p.tp > 1) {
+                            __threadfence_system();
+                            __syncwarp();
+                            if (lane == 0) signal_tile();
                         }
                     }
                     if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
@@ -817,8 +889,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     if (n < p.N) {
 #pragma unroll
                         for (int m = 0; m < MC; ++m)
-                            if (m < p.M) p.D[(size_t)m * p.N + n] = f32_to_t<BF16>(acc[j][m]);
+                            if (m < p.M) store_out(m, n, f32_to_t<BF16>(acc[j][m]));
                     }
+                }
+                if (p.tp > 1) {      // whole tile written by the apply warps: one arrival per rank once all of them are done
+                    __threadfence_system();
+                    asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
+                    if (warp == kApplyWarp0 && lane == 0) signal_tile();
                 }
             } else {
                 // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left zero
@@ -892,48 +969,120 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         int chunk = grp * CPS;             // global chunk index of (stage i, c = 0)
         int aslot = chunk % AS;
         uint32_t aphase = ((uint32_t)(chunk / AS) & 1u) ^ 1u;
-        for (int i = grp; i < n_it; i += DQG) {
-            wait(smem_u32(&ctl->full[stage]), fphase, p, DSITE_FULL);
-            DPROF_ADD(dw_full, dt);
-            const uint32_t row = ring + stage * kStageBytes + wrow;
-#pragma unroll
-            for (int c = 0; c < CPS; ++c) {
-                if (c == CPS - 1) {
-                    if (i >= AS / CPS) {
-                        wait(smem_u32(&ctl->empty[tstage]), tphase, p, DSITE_AEMPTY);
-                        tstage += DQG;
-                        if (tstage >= S) { tstage -= S; tphase ^= 1u; }
-                    }
-                } else {
-                    wait(smem_u32(&ctl->a_empty[aslot]), aphase, p, DSITE_AEMPTY, i * 1000 + n_it);
+        if constexpr (BITS == 4) {
+            // Software-pipelined (4-bit; CPS == 1, one A slot per stage): a warp's turn on stage i is
+            //   [look-ups of quads 0,1] -> wait "A slot free" -> 4 x tcgen05.st -> [look-ups of quads 2,3] -> 4 x tcgen05.st
+            //   -> (if stage i + DQG has landed) load its four 16-byte quads -> tcgen05.wait::st, arrive a_full
+            // so the slot wait sits behind 32 look-ups already in flight and the packed words of the next turn are on
+            // their way while the tensor-memory stores drain; the shared-memory pipe, which bounds this role
+            // (640 wavefronts per stage), does not idle across the hand-over.
+            static_assert(CPS == 1 || BITS != 4, "pipelined loop: one chunk per stage");
+            uint4 v0, v1, v2, v3;
+            bool have = false;             // v0..v3 hold the quads of the stage this turn converts
+            for (int i = grp; i < n_it; i += DQG) {
+                const uint32_t row = ring + stage * kStageBytes + wrow;
+                if (!have) {
+                    wait(smem_u32(&ctl->full[stage]), fphase, p, DSITE_FULL);
+                    v0 = lds128(row + (uint32_t)(((4 * hw) ^ xq) << 4));
+                    v1 = lds128(row + (uint32_t)(((4 * hw + 1) ^ xq) << 4));
+                    v2 = lds128(row + (uint32_t)(((4 * hw + 2) ^ xq) << 4));
+                    v3 = lds128(row + (uint32_t)(((4 * hw + 3) ^ xq) << 4));
                 }
-                DPROF_ADD(dw_aempty, dt);
-                tc_fence_after();
-                const uint32_t tcol = tmem + lane_sel + aslot * kACols;
+                DPROF_ADD(dw_full, dt);
+                const uint32_t tcol = tmem + lane_sel + aslot * kACols + hw * 16;
+                // first 32 look-ups: results stay in registers until the slot is known to be free
+                const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                uint32_t r[4][8];
                 if (do_dq) {
-                    if constexpr (BITS == 4) {
-                        // this warp's 16 k-pairs of the stage: 16-byte quads 4*hw .. 4*hw + 3 of row L
-                        Piece<4>::run<CK2>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
-                        Piece<4>::run<CK2>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
-                    } else {
-                        // half stage c: quad c*4 + sw
-                        Piece<2>::run(row, (c * 4 + hw) ^ xq, lut, lane4, tcol + hw * 4);
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        r[0][x] = lds32(lut + code_lane<0>(w[x], lane4));
+                        r[1][x] = lds32(lut + code_lane<1>(w[x], lane4));
+                        r[2][x] = lds32(lut + code_lane<2>(w[x], lane4));
+                        r[3][x] = lds32(lut + code_lane<3>(w[x], lane4));
                     }
                 }
                 DPROF_ADD(dw_piece, dt);
+                if (i >= AS) {
+                    wait(smem_u32(&ctl->empty[tstage]), tphase, p, DSITE_AEMPTY);
+                    tstage += DQG;
+                    if (tstage >= S) { tstage -= S; tphase ^= 1u; }
+                }
+                DPROF_ADD(dw_aempty, dt);
+                tc_fence_after();
+                if (do_dq) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tmem_st_x8(tcol + j * CK2, r[j]);
+                    piece4_from_regs<CK2>(v2, v3, lut, lane4, tcol + 8);
+                }
+                DPROF_ADD(dw_piece, dt);
+                // next turn: ring slot / parity of stage i + DQG
+                int nstage = stage + DQG;
+                uint32_t nphase = fphase;
+                if (nstage >= S) { nstage -= S; nphase ^= 1u; }
+                have = false;
+                if (i + DQG < n_it && mbar_try_wait(smem_u32(&ctl->full[nstage]), nphase)) {
+                    const uint32_t nrow = ring + nstage * kStageBytes + wrow;
+                    v0 = lds128(nrow + (uint32_t)(((4 * hw) ^ xq) << 4));
+                    v1 = lds128(nrow + (uint32_t)(((4 * hw + 1) ^ xq) << 4));
+                    v2 = lds128(nrow + (uint32_t)(((4 * hw + 2) ^ xq) << 4));
+                    v3 = lds128(nrow + (uint32_t)(((4 * hw + 3) ^ xq) << 4));
+                    have = true;
+                }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
-                if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                aslot += DQG;              // the other set converts the stages in between
+                if (aslot >= AS) aslot -= AS;
+                stage = nstage;
+                fphase = nphase;
                 DPROF_ADD(dw_st, dt);
             }
-            // skip the chunks of the stages the other set converts
-#pragma unroll
-            for (int x = 0; x < (DQG - 1) * CPS; ++x)
-                if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
-            stage += DQG;
-            if (stage >= S) { stage -= S; fphase ^= 1u; }
+        } else {
+        for (int i = grp; i < n_it; i += DQG) {
+                wait(smem_u32(&ctl->full[stage]), fphase, p, DSITE_FULL);
+                DPROF_ADD(dw_full, dt);
+                const uint32_t row = ring + stage * kStageBytes + wrow;
+    #pragma unroll
+                for (int c = 0; c < CPS; ++c) {
+                    if (c == CPS - 1) {
+                        if (i >= AS / CPS) {
+                            wait(smem_u32(&ctl->empty[tstage]), tphase, p, DSITE_AEMPTY);
+                            tstage += DQG;
+                            if (tstage >= S) { tstage -= S; tphase ^= 1u; }
+                        }
+                    } else {
+                        wait(smem_u32(&ctl->a_empty[aslot]), aphase, p, DSITE_AEMPTY, i * 1000 + n_it);
+                    }
+                    DPROF_ADD(dw_aempty, dt);
+                    tc_fence_after();
+                    const uint32_t tcol = tmem + lane_sel + aslot * kACols;
+                    if (do_dq) {
+                        if constexpr (BITS == 4) {
+                            // this warp's 16 k-pairs of the stage: 16-byte quads 4*hw .. 4*hw + 3 of row L
+                            Piece<4>::run<CK2>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, tcol + hw * 16);
+                            Piece<4>::run<CK2>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, tcol + hw * 16 + 8);
+                        } else {
+                            // half stage c: quad c*4 + sw
+                            Piece<2>::run(row, (c * 4 + hw) ^ xq, lut, lane4, tcol + hw * 4);
+                        }
+                    }
+                    DPROF_ADD(dw_piece, dt);
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
+                    if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                    DPROF_ADD(dw_st, dt);
+                }
+                // skip the chunks of the stages the other set converts
+    #pragma unroll
+                for (int x = 0; x < (DQG - 1) * CPS; ++x)
+                    if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                stage += DQG;
+                if (stage >= S) { stage -= S; fphase ^= 1u; }
+            }
         }
 #ifdef FB_PROFILE
         if (lane == 0 && (warp == 0 || warp == 5)) {

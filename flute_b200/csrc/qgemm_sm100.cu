@@ -1098,4 +1098,24 @@ int qgemm_launch(const QgemmArgs& a, cudaStream_t stream) {
     return FB_ERR_BITS;
 }
 
+
+// Which kernel qgemm_launch picks for a problem (automatic selection; reporting only).
+const char* qgemm_dispatch_name(int M, int num_bits, bool bf16) {
+    QgemmArgs a{};
+    a.M = M; a.num_bits = num_bits; a.bf16 = bf16; a.variant = -1;
+    if (M >= 1 && qgemm_decode_supported(a)) {
+        if (num_bits == 4) return M == 1 ? (bf16 ? "fb::dec::qgemm_decode_kernel<4,bf16,MC=1>" : "fb::dec::qgemm_decode_kernel<4,f16,MC=1>")
+                                         : (bf16 ? "fb::dec::qgemm_decode_kernel<4,bf16,MC=4>" : "fb::dec::qgemm_decode_kernel<4,f16,MC=4>");
+        return M == 1 ? (bf16 ? "fb::dec::qgemm_decode_kernel<2,bf16,MC=1>" : "fb::dec::qgemm_decode_kernel<2,f16,MC=1>")
+                      : (bf16 ? "fb::dec::qgemm_decode_kernel<2,bf16,MC=4>" : "fb::dec::qgemm_decode_kernel<2,f16,MC=4>");
+    }
+    if (qgemm_prefill_supported(a)) return bf16 ? "fb::pre::qgemm_prefill_kernel<bf16>" : "fb::pre::qgemm_prefill_kernel<f16>";
+    switch (num_bits) {
+        case 4: return bf16 ? "fb::qgemm_sm100_kernel<4,bf16,LARGE>" : "fb::qgemm_sm100_kernel<4,f16,LARGE>";
+        case 3: return bf16 ? "fb::qgemm_sm100_kernel<3,bf16,LARGE>" : "fb::qgemm_sm100_kernel<3,f16,LARGE>";
+        case 2: return bf16 ? "fb::qgemm_sm100_kernel<2,bf16,LARGE>" : "fb::qgemm_sm100_kernel<2,f16,LARGE>";
+    }
+    return "unsupported";
+}
+
 }  // namespace fb

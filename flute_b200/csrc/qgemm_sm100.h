@@ -86,6 +86,7 @@ inline size_t prefill_scratch_bytes(int num_sms) { return (size_t)num_sms * 2 * 
 bool qgemm_prefill_supported(const QgemmArgs& a);
 int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream);
 int qgemm_max_mb(int bits);
+const char* qgemm_dispatch_name(int M, int num_bits, bool bf16);
 int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                  uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
 

@@ -113,6 +113,10 @@ FLUTE_B200_API int flute_b200_num_sms(int device);
 /* Largest activation-row tile (MMA N) the engine uses for `num_bits`; informational. */
 FLUTE_B200_API int flute_b200_max_batch_tile(int num_bits);
 
+/* Name of the kernel the automatic dispatch of flute_b200_qgemm selects for (M, num_bits, dtype) -- reporting only
+ * (bench.py's roofline.kernel); a static string. */
+FLUTE_B200_API const char* flute_b200_dispatch_name(int M, int num_bits, int dtype);
+
 FLUTE_B200_API const char* flute_b200_last_error(void);
 FLUTE_B200_API const char* flute_b200_error_string(int code);
 FLUTE_B200_API int flute_b200_version(void);

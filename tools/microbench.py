@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--ablate", type=int, default=0)
+    ap.add_argument("--slack", type=int, default=0, help="SMs left idle per launch (grid = SMs - slack)")
     ap.add_argument("--l2pf", type=int, default=-1, help="decode kernel: L2 prefetch distance in stages (-1 = engine's choice)")
     ap.add_argument("--trace", type=int, default=0, help="print a per-CTA timeline of one isolated launch")
     args = ap.parse_args()
@@ -49,7 +50,7 @@ def main():
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float16
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
     ws = utils.get_workspace_streamk(dev)
-    _lib.lib.flute_b200_set_variant((args.variant & 0xff) | (args.ablate << 8) | ((args.l2pf + 1) << 16))
+    _lib.lib.flute_b200_set_variant((args.variant & 0xff) | (args.ablate << 8) | ((args.l2pf + 1) << 16) | (args.slack << 24))
     bits, group = args.bits, args.group
     table = torch.randn(2 ** bits, device=dev).to(dt)
     table2 = utils.make_qmap2_from_qmap(table)
