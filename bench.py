@@ -396,7 +396,7 @@ def run_own(args):
     tpx = None
     if tp > 1:
         progress("tensor-parallel exchange: symmetric memory rendezvous")
-        tpx = parallel.FusedGather(dev, rank, tp, [(name, M, N) for name, N, K in SHAPES], torch.bfloat16)
+        tpx = parallel.FusedGather(dev, rank, tp, [(name, M, N, LAYERS) for name, N, K in SHAPES], torch.bfloat16)
     bufs = {name: torch.empty((M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
     gathered = {name: torch.empty((tp, M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
 

@@ -31,6 +31,10 @@ EXPORTS = (
     "flute_b200_set_trace_buffer",
     "flute_b200_set_variant",
     "flute_b200_dispatch_name",
+    "flute_b200_qgemm_tp",
+    "flute_b200_tp_tiles",
+    "flute_b200_tp_advance",
+    "flute_b200_tp_wait",
 )
 
 F16, BF16 = 0, 1
@@ -38,6 +42,14 @@ FLAG_PDL = 1
 FLAG_STATIC_WEIGHTS = 2
 
 _vp, _i, _sz, _l = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_long
+_u = ctypes.c_uint
+
+
+class TpDesc(ctypes.Structure):
+    """`flute_b200_tp` of include/flute_b200.h (tensor-parallel fused exchange descriptor)."""
+    _fields_ = [("tp", _i), ("rank", _i), ("n_total", _i), ("out_peers", _vp * 8), ("flag_peers", _vp * 8),
+                ("in_flag", _vp), ("in_per_step", _u), ("in_offset", _u), ("epoch", _vp)]
+
 
 
 def _load() -> ctypes.CDLL:
@@ -76,6 +88,15 @@ def _load() -> ctypes.CDLL:
     lib.flute_b200_set_variant.restype = None
     lib.flute_b200_set_trace_buffer.argtypes = [_vp]
     lib.flute_b200_set_trace_buffer.restype = None
+    lib.flute_b200_qgemm_tp.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
+                                        ctypes.POINTER(TpDesc)]
+    lib.flute_b200_qgemm_tp.restype = _i
+    lib.flute_b200_tp_tiles.argtypes = [_i, _i]
+    lib.flute_b200_tp_tiles.restype = _i
+    lib.flute_b200_tp_advance.argtypes = [_vp, _i, _vp]
+    lib.flute_b200_tp_advance.restype = _i
+    lib.flute_b200_tp_wait.argtypes = [_vp, _u, _u, _vp, _i, _vp]
+    lib.flute_b200_tp_wait.restype = _i
     lib.flute_b200_dispatch_name.argtypes = [_i, _i, _i]
     lib.flute_b200_dispatch_name.restype = ctypes.c_char_p
     lib.flute_b200_check.argtypes = [_i]

@@ -108,7 +108,7 @@ int validate_quant(int N, int K, int num_bits, int group_size, int tile_P, int d
 int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* table2, void* workspace,
               size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size, int tile_P, int dtype,
               int flags, int device, void* stream, int force_mb, int force_stages, int force_grid, int force_streamk,
-              void* dbg) {
+              void* dbg, const flute_b200_tp* tp = nullptr) {
     int rc = validate_quant(N, K, num_bits, group_size, tile_P, dtype);
     if (rc != FB_OK) return rc;
     if (M < 0) return fail(FB_ERR_SHAPE, "M = %d is negative", M);
@@ -141,6 +141,9 @@ int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* 
     a.variant = g_variant;
     a.ablate = g_ablate;
     a.l2_prefetch = g_l2_prefetch;
+    a.tp = tp;
+    if (tp != nullptr && tp->tp > 1 && !(M <= 4 && (num_bits == 4 || num_bits == 2)))
+        return fail(FB_ERR_SHAPE, "tensor-parallel fused exchange: decode shapes only (M <= 4 at 2/4 bits), got M=%d bits=%d", M, num_bits);
     a.timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
     a.force_mb = force_mb; a.force_stages = force_stages; a.force_grid = force_grid; a.force_streamk = force_streamk;
     if (a.force_grid <= 0 && g_grid_slack > 0 && g_grid_slack < a.num_sms) a.force_grid = a.num_sms - g_grid_slack;
@@ -167,6 +170,48 @@ int flute_b200_qgemm(const void* A, const void* Q, void* D, const void* S, const
     (void)table;   // semantics live in table2 (every reference template is a Vectorized* mode, codegen_utils.py:97-102)
     return run_qgemm(A, Q, D, S, table2, workspace, workspace_bytes, M, N, K, num_bits, group_size, tile_P, dtype, flags,
                      device, stream, 0, 0, 0, -1, nullptr);
+}
+
+int flute_b200_qgemm_tp(const void* A, const void* Q, const void* S, const void* table, const void* table2, void* workspace,
+                        size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size, int tile_P, int dtype,
+                        int flags, int device, void* stream, const flute_b200_tp* tp) {
+    (void)table;
+    if (tp == nullptr) return fail(FB_ERR_NULL, "null tensor-parallel descriptor");
+    if (tp->tp < 1 || tp->tp > 8 || tp->rank < 0 || tp->rank >= tp->tp) return fail(FB_ERR_SHAPE, "tp=%d rank=%d out of range", tp->tp, tp->rank);
+    if (tp->n_total != tp->tp * N) return fail(FB_ERR_SHAPE, "n_total=%d is not tp*N=%d", tp->n_total, tp->tp * N);
+    if (tp->out_peers[tp->rank] == nullptr) return fail(FB_ERR_NULL, "null gathered-output pointer");
+    // the local slice pointer doubles as D for validation; with tp == 1 it is simply the output
+    void* D_local = static_cast<char*>(tp->out_peers[tp->rank]);
+    return run_qgemm(A, Q, D_local, S, table2, workspace, workspace_bytes, M, N, K, num_bits, group_size, tile_P, dtype, flags,
+                     device, stream, 0, 0, 0, -1, nullptr, tp);
+}
+
+int flute_b200_tp_tiles(int N, int num_bits) {
+    const int cols = fb::decode_tile_columns(num_bits);
+    if (cols <= 0 || N <= 0) return FB_ERR_SHAPE;
+    return (N + cols - 1) / cols;
+}
+
+int flute_b200_tp_advance(unsigned* epoch, int device, void* stream) {
+    if (epoch == nullptr) return fail(FB_ERR_NULL, "null epoch pointer");
+    int rc = probe_device(device);
+    if (rc != FB_OK) return rc;
+    DeviceGuard guard(device);
+    if (guard.rc != FB_OK) return fail(guard.rc, "cudaSetDevice(%d) failed", device);
+    rc = fb::tp_advance_launch(epoch, static_cast<cudaStream_t>(stream));
+    return rc == FB_OK ? FB_OK : fail(rc, "tp_advance launch failed");
+}
+
+int flute_b200_tp_wait(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, int device, void* stream) {
+    if (flag == nullptr || epoch == nullptr) return fail(FB_ERR_NULL, "null flag / epoch pointer");
+    int rc = probe_device(device);
+    if (rc != FB_OK) return rc;
+    DeviceGuard guard(device);
+    if (guard.rc != FB_OK) return fail(guard.rc, "cudaSetDevice(%d) failed", device);
+    const uint64_t timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
+    rc = fb::tp_wait_launch(flag, per_step, offset, epoch, timeout_ns, diag_for(device, static_cast<cudaStream_t>(stream)),
+                            static_cast<cudaStream_t>(stream));
+    return rc == FB_OK ? FB_OK : fail(rc, "tp_wait launch failed");
 }
 
 int flute_b200_qgemm_debug(const void* A, const void* Q, void* D, const void* S, const void* table2, void* workspace,

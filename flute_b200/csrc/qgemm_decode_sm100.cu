@@ -1127,6 +1127,18 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.ablate = a.ablate;
     p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
     p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : 0;
+    if (a.tp != nullptr && a.tp->tp > 1) {
+        if (a.tp->tp > 8 || a.tp->rank < 0 || a.tp->rank >= a.tp->tp || a.tp->n_total != a.tp->tp * a.N || a.tp->epoch == nullptr)
+            return FB_ERR_SHAPE;
+        p.tp = a.tp->tp; p.rank = a.tp->rank; p.n_total = a.tp->n_total;
+        for (int r = 0; r < p.tp; ++r) {
+            if (a.tp->out_peers[r] == nullptr || a.tp->flag_peers[r] == nullptr) return FB_ERR_NULL;
+            p.out_peers[r] = static_cast<uint16_t*>(a.tp->out_peers[r]);
+            p.flag_peers[r] = a.tp->flag_peers[r];
+        }
+        p.in_flag = a.tp->in_flag; p.in_per_step = a.tp->in_per_step; p.in_offset = a.tp->in_offset;
+        p.epoch = a.tp->epoch;
+    }
 
     const uint32_t fixed = F::SC_SLOTS * TN * 16 + F::LUTB + sizeof(Ctl) + 1024 /*alignment slack*/;
     int stages = (int)((kSmemBudget - fixed) / kStageBytes);
@@ -1192,6 +1204,35 @@ static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace dec
+
+int decode_tile_columns(int bits) { return bits == 4 ? dec::DCfg<4>::NJ * 128 : bits == 2 ? dec::DCfg<2>::NJ * 128 : 0; }
+
+namespace dec {
+__global__ void tp_advance_kernel(unsigned* epoch) { *epoch += 1u; }
+__global__ void tp_wait_kernel(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, uint64_t timeout_ns,
+                               Diag* diag) {
+    const unsigned expected = (ld_acquire_sys_u32(epoch) - 1u) * per_step + offset;
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while ((int)(ld_acquire_sys_u32(flag) - expected) < 0) {
+        if ((++spins & 0xff) == 0 && timeout_ns != 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) wait_timeout(diag, DSITE_FULL, 0u, expected, -3);
+        }
+    }
+}
+}  // namespace dec
+
+int tp_advance_launch(unsigned* epoch, cudaStream_t stream) {
+    dec::tp_advance_kernel<<<1, 1, 0, stream>>>(epoch);
+    return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_LAUNCH;
+}
+int tp_wait_launch(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, uint64_t timeout_ns, Diag* diag,
+                   cudaStream_t stream) {
+    dec::tp_wait_kernel<<<1, 1, 0, stream>>>(flag, per_step, offset, epoch, timeout_ns, diag);
+    return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_LAUNCH;
+}
 
 bool qgemm_decode_supported(const QgemmArgs& a) {
     // Dispatched automatically for M <= 4.  For 5 <= M <= 16 (4-bit) the 16-accumulator variant works (tests pin it

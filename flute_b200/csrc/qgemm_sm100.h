@@ -41,6 +41,7 @@ struct QgemmArgs {
     int ablate;    // perf ablation bits (tests only): 1 skip MMA issue, 2 skip dequant math
     int variant;   // -1 auto; general kernel: 0 LARGE (1 CTA/SM), 1 SMALL (2 CTAs/SM); decode kernel: 2 also 5 <= M <= 16
     int l2_prefetch;   // decode kernel: L2 prefetch distance in stages, -1 = engine's choice
+    const flute_b200_tp* tp;   // tensor-parallel fused exchange (decode kernel only), or nullptr
 };
 
 // Kernel parameters (passed by value).
@@ -86,6 +87,10 @@ inline size_t prefill_scratch_bytes(int num_sms) { return (size_t)num_sms * 2 * 
 bool qgemm_prefill_supported(const QgemmArgs& a);
 int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream);
 int qgemm_max_mb(int bits);
+int decode_tile_columns(int bits);   // output columns per decode-kernel tile (arrival unit of the fused exchange)
+int tp_advance_launch(unsigned* epoch, cudaStream_t stream);
+int tp_wait_launch(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, uint64_t timeout_ns, Diag* diag,
+                   cudaStream_t stream);
 const char* qgemm_dispatch_name(int M, int num_bits, bool bf16);
 int make_tmap_2d(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, uint64_t inner, uint64_t outer,
                  uint64_t row_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);

@@ -8,7 +8,8 @@ all-gather of the [M, N/world] outputs (north_star); K is never sharded.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -49,3 +50,97 @@ def all_gather_columns(local: torch.Tensor, group: Optional[dist.ProcessGroup] =
     if M == 1:
         return out.view(1, world * n_loc)          # rank-major == column order when there is one row
     return out.permute(1, 0, 2).reshape(M, world * n_loc)
+
+
+class FusedGather:
+    """The forward exchange of a column-sharded linear, fused into the GEMM.
+
+    One symmetric-memory allocation per rank (torch.distributed._symmetric_memory: CUDA VMM buffers mapped into every
+    peer over NVLink) holds, for every named output, the gathered activation buffer [M, N_total] and its arrival
+    counter.  `qgemm` calls `flute_b200_qgemm_tp`: the kernel's epilogue stores this rank's [M, N_total / tp] slice
+    into every rank's buffer and bumps every rank's counter; when the activations passed in live in one of these
+    buffers, the kernel first waits for that buffer's counter.  There is no collective kernel and nothing to
+    synchronise on the host, so a whole token step captures into one CUDA graph.
+
+        fg = FusedGather(dev, rank, tp, [("qkv", 1, 6144, 32), ...], torch.bfloat16)   # name, M, N_total, uses per step
+        fg.begin_step();  y = fg.qgemm(x, Q_r, S_r, table, table2, ws, "qkv", n_loc, K, 4, 64, flags);  ...;  fg.end_step("down")
+
+    Every rank must issue the same sequence of calls per step; each named buffer is written `uses` times per step.
+    """
+
+    def __init__(self, device: torch.device, rank: int, tp: int, outputs: Sequence[Tuple[str, int, int, int]],
+                 dtype: torch.dtype, group: Optional[dist.ProcessGroup] = None, num_bits: int = 4) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.device, self.rank, self.tp, self.dtype, self.num_bits = device, rank, tp, dtype, num_bits
+        group = group if group is not None else dist.group.WORLD
+        flag_bytes = 128 * len(outputs)
+        offs, off = {}, flag_bytes
+        for name, M, n_total, uses in outputs:
+            offs[name] = off
+            off += (M * n_total * 2 + 255) // 256 * 256
+        self.buf = symm_mem.empty(off, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                      # every rank's counters are zero before anyone's first store can land
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.out: Dict[str, dict] = {}
+        for i, (name, M, n_total, uses) in enumerate(outputs):
+            n_loc = n_total // tp
+            arrivals = tp * _lib.lib.flute_b200_tp_tiles(n_loc, num_bits)
+            view = self.buf[offs[name]:offs[name] + M * n_total * 2].view(dtype).view(M, n_total)
+            self.out[name] = dict(M=M, n_total=n_total, uses=uses, arrivals=arrivals, view=view,
+                                  base=ptrs[rank] + offs[name], nbytes=M * n_total * 2,
+                                  out_peers=[p + offs[name] for p in ptrs], flag_peers=[p + 128 * i for p in ptrs],
+                                  calls=0)
+
+    def begin_step(self) -> None:
+        for o in self.out.values():
+            o["calls"] = 0
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib.check(self._lib.lib.flute_b200_tp_advance(self.epoch.data_ptr(), self.device.index, st))
+
+    def _guard_of(self, x: torch.Tensor):
+        """(flag pointer, arrivals per step, arrivals needed) of the gathered buffer `x` lives in, or (None, 0, 0)."""
+        p = x.data_ptr()
+        for o in self.out.values():
+            if o["base"] <= p < o["base"] + o["nbytes"]:
+                return o["flag_peers"][self.rank], o["uses"] * o["arrivals"], o["calls"] * o["arrivals"]
+        return None, 0, 0
+
+    def qgemm(self, x: torch.Tensor, Q: torch.Tensor, S: torch.Tensor, table: torch.Tensor, table2: torch.Tensor,
+              workspace: torch.Tensor, name: str, n_loc: int, K: int, num_bits: int, group_size: int, flags: int,
+              tile_P: int = 32) -> torch.Tensor:
+        _lib = self._lib
+        o = self.out[name]
+        M = x.shape[0]
+        if M != o["M"] or n_loc * self.tp != o["n_total"] or not x.is_contiguous():
+            raise ValueError("flute_b200: FusedGather.qgemm shape mismatch")
+        d = _lib.TpDesc()
+        d.tp, d.rank, d.n_total = self.tp, self.rank, o["n_total"]
+        for r in range(self.tp):
+            d.out_peers[r] = o["out_peers"][r]
+            d.flag_peers[r] = o["flag_peers"][r]
+        flag, per_step, offset = self._guard_of(x)
+        d.in_flag = flag
+        d.in_per_step, d.in_offset = per_step, offset
+        d.epoch = self.epoch.data_ptr()
+        code = _lib.BF16 if self.dtype == torch.bfloat16 else _lib.F16
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        rc = _lib.lib.flute_b200_qgemm_tp(x.data_ptr(), Q.data_ptr(), S.data_ptr(), table.data_ptr(), table2.data_ptr(),
+                                          workspace.data_ptr(), workspace.numel(), M, n_loc, K, num_bits, group_size, tile_P,
+                                          code, flags, self.device.index, st, ctypes.byref(d))
+        _lib.check(rc)
+        o["calls"] += 1
+        return o["view"]
+
+    def end_step(self, name: str) -> None:
+        """Stream-ordered wait for the last write of `name` in this step (before a non-flute consumer reads it)."""
+        o = self.out[name]
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.lib.flute_b200_tp_wait(o["flag_peers"][self.rank], o["uses"] * o["arrivals"], o["calls"] * o["arrivals"],
+                                              self.epoch.data_ptr(), self.device.index, st)
+        self._lib.check(rc)

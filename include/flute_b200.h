@@ -113,6 +113,47 @@ FLUTE_B200_API int flute_b200_num_sms(int device);
 /* Largest activation-row tile (MMA N) the engine uses for `num_bits`; informational. */
 FLUTE_B200_API int flute_b200_max_batch_tile(int num_bits);
 
+/*
+ * Tensor-parallel column shard with the exchange fused into the GEMM (the reference's only
+ * forward collective is the all-gather vLLM's ColumnParallelLinear adds around flute.qgemm_simple,
+ * flute/integrations/vllm_utils.py:242-244,328-349).
+ *
+ * Rank r of tp owns output columns [r*N, (r+1)*N) of an n_total = tp*N wide linear (its Q / S row slices,
+ * flute_b200/parallel.py).  flute_b200_qgemm_tp computes them like flute_b200_qgemm, but the kernel's epilogue stores
+ * the slice straight into EVERY rank's gathered output buffer [M, n_total] (out_peers: peer-mapped device pointers,
+ * e.g. torch symmetric memory over NVLink) and then bumps that buffer's arrival counter on every rank
+ * (flag_peers; red.release.sys).  If `in_flag` is non-NULL the activations A live in such a gathered buffer: the
+ * kernel waits (ld.acquire.sys) until in_flag has received all of this step's arrivals before it reads A.  Counters
+ * only ever grow: the expected value is (*epoch - 1) * in_per_step + in_offset, where *epoch is the step number
+ * (>= 1, advanced once per step by flute_b200_tp_advance on the same stream), in_per_step the arrivals the buffer
+ * receives per step and in_offset the arrivals it must have received within the step before this call may read it
+ * (a buffer written by L producing calls per step: in_per_step = L * a, in_offset = (l + 1) * a for the consumer of
+ * the l-th, with a = tp * flute_b200_tp_tiles(N_producer, num_bits)).  No collective kernel and no host
+ * synchronisation are involved; the call is CUDA-graph capturable.  Decode shapes only (M <= 4 at 2 / 4 bits).
+ */
+typedef struct flute_b200_tp {
+    int tp, rank;
+    int n_total;                 /* columns of the gathered output = tp * N */
+    void* out_peers[8];          /* every rank's [M, n_total] buffer for THIS output */
+    unsigned* flag_peers[8];     /* every rank's arrival counter for THIS output */
+    const unsigned* in_flag;     /* this rank's arrival counter guarding A, or NULL */
+    unsigned in_per_step;
+    unsigned in_offset;
+    const unsigned* epoch;       /* device word holding the step number */
+} flute_b200_tp;
+
+FLUTE_B200_API int flute_b200_qgemm_tp(const void* A, const void* Q, const void* S, const void* table, const void* table2,
+                        void* workspace, size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size,
+                        int tile_P, int dtype, int flags, int device, void* stream, const flute_b200_tp* tp);
+/* Arrivals ONE rank contributes to a gathered buffer per producing call: its output-tile count for N local columns. */
+FLUTE_B200_API int flute_b200_tp_tiles(int N, int num_bits);
+/* ++*epoch on `stream` (one tiny kernel): call once at the start of every step, before the step's first qgemm_tp. */
+FLUTE_B200_API int flute_b200_tp_advance(unsigned* epoch, int device, void* stream);
+/* Stream-ordered wait until `flag` has received (*epoch - 1) * per_step + offset arrivals: for consumers of a gathered
+ * buffer that are not flute_b200_qgemm_tp calls (the copy of the step's result, another library's kernel). */
+FLUTE_B200_API int flute_b200_tp_wait(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, int device,
+                       void* stream);
+
 /* Name of the kernel the automatic dispatch of flute_b200_qgemm selects for (M, num_bits, dtype) -- reporting only
  * (bench.py's roofline.kernel); a static string. */
 FLUTE_B200_API const char* flute_b200_dispatch_name(int M, int num_bits, int dtype);
