@@ -58,6 +58,16 @@ enum {
 /*
  * D[M,N] = A[M,K] . W_hat[K,N],  W_hat[k,n] = round_T(table2[code].{lo,hi} * S[n, k / group_size]).
  *
+ * Numerics.  M >= 5 (general and prefill kernels): exactly the formula above, fp32 accumulation -- the reference's
+ * arithmetic (packbits_utils.hpp:105,139).  M <= 4 at 2 / 4 bits (decode kernel): the group scale is applied to the fp32
+ * partial sum of each group instead, D[m,n] = sum_g S[n,g] * (sum_{k in g} A[m,k] * table2[code(k,n)]), i.e. the product
+ * table*S is NOT rounded to T first.  With a one-hot A this still yields round_T(table*S) exactly (bit-identical to
+ * the reference's identity reconstruction; tested), for general A it differs from the M >= 5 result by rounding only
+ * (bounded in tests/test_qgemm_gpu.py::test_decode_vs_prefill_numerics_bound: < 1.0e-3 fp16 / 5.5e-3 bf16 relative, inside
+ * the reference's own 2.0e-3 / 1.1e-2 acceptance bound).  Consequence: results are not batch-invariant across M = 4 | 5.
+ * Split-K partial sums are added in fp32 in arrival order, so results are reproducible to fp32 reduction-order noise only
+ * (as with the reference's Stream-K fix-up).
+ *
  * Replaces  torch.ops.flute.qgemm_raw_simple -> qgemm_raw<T,NumBits,GroupSize> -> _qgemm_raw -> qgemm_host
  *           (flute/csrc/qgemm.cpp:44-198, qgemm_kernel_raw_generated.cu:15-768, qgemm_kernel.hpp:841-939).
  *   A         [M, K]  T, row-major, contiguous                      (qgemm.cpp:71,110)

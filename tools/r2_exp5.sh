@@ -30,3 +30,6 @@ for sh in small gateup; do
   FLUTE_B200_PROFILE=1 timeout 200 python tools/microbench.py --M 1 --shapes $sh --trace 2 --reps 3 >> "$OUT/trace.log" 2>&1
 done
 grep -v "producer\|mma wait\|mma issue\|dq5" "$OUT/trace.log" | tail -60
+echo "== prefill trace gateup M=4096" > "$OUT/trace_prefill.log"
+FLUTE_B200_PROFILE=1 timeout 200 python tools/microbench.py --M 4096 --shapes gateup --trace 1 --reps 1 >> "$OUT/trace_prefill.log" 2>&1
+grep -v "^     start\|^     setup\|exit" "$OUT/trace_prefill.log" | tail -30
