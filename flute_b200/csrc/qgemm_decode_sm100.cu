@@ -969,14 +969,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         int chunk = grp * CPS;             // global chunk index of (stage i, c = 0)
         int aslot = chunk % AS;
         uint32_t aphase = ((uint32_t)(chunk / AS) & 1u) ^ 1u;
-        if constexpr (BITS == 4) {
+        if (BITS == 4 && !(p.ablate & 8)) {
             // Software-pipelined (4-bit; CPS == 1, one A slot per stage): a warp's turn on stage i is
             //   [look-ups of quads 0,1] -> wait "A slot free" -> 4 x tcgen05.st -> [look-ups of quads 2,3] -> 4 x tcgen05.st
             //   -> (if stage i + DQG has landed) load its four 16-byte quads -> tcgen05.wait::st, arrive a_full
             // so the slot wait sits behind 32 look-ups already in flight and the packed words of the next turn are on
             // their way while the tensor-memory stores drain; the shared-memory pipe, which bounds this role
             // (640 wavefronts per stage), does not idle across the hand-over.
-            static_assert(CPS == 1 || BITS != 4, "pipelined loop: one chunk per stage");
             uint4 v0, v1, v2, v3;
             bool have = false;             // v0..v3 hold the quads of the stage this turn converts
             for (int i = grp; i < n_it; i += DQG) {
@@ -1144,7 +1143,10 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     int stages = (int)((kSmemBudget - fixed) / kStageBytes);
     if (stages > F::MAX_STAGES) stages = F::MAX_STAGES;
     if (a.force_stages > 0 && a.force_stages < stages) stages = a.force_stages;
-    if (stages < 2) return FB_ERR_INTERNAL;
+    // The dequantisers wait for the MMAs of stage i - A_SLOTS/CPS on that stage's ring barrier; a shallower ring would let
+    // the barrier run two phases ahead of that wait (parity aliasing -> deadlock), so the ring is at least that deep.
+    constexpr int kMinStages = (F::A_SLOTS / F::CPS > 2) ? F::A_SLOTS / F::CPS : 2;
+    if (stages < kMinStages) stages = kMinStages;
     p.stages = stages;
     const uint32_t smem_bytes = stages * kStageBytes + fixed;
 

@@ -93,6 +93,7 @@ struct Params {
     int n_tiles, m_tiles, k_iters;
     int stages;
     int streamk;
+    int dp_tiles;            // Stream-K: the first dp_tiles tiles are taken whole (dp_tiles / grid per CTA), only the rest is split
     int tma_scales;
     size_t scratch_offset;   // per-CTA partial-tile slots (2 per CTA) at the end of the workspace
 };
@@ -190,27 +191,43 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, int tile) {
     c.mt = r - c.fp * p.m_tiles;
     return c;
 }
-__device__ __forceinline__ Range cta_range(const Params& p, int b, int grid) {
+// Work of CTA b: part 0 = whole tiles, part 1 = its share of the Stream-K region (the tiles after dp_tiles, split at
+// stage granularity).  Whole tiles first keeps the split -- and its fix-up through global scratch -- to the remainder
+// that does not fill a wave: at 4096 x 4096, M = 4096 (512 tiles on 148 CTAs) 444 tiles need no fix-up and 68 are
+// shared by ~2 CTAs each, instead of every CTA boundary falling inside a tile.
+__device__ __forceinline__ Range cta_part(const Params& p, int b, int grid, int part) {
     Range r;
-    if (p.streamk) {
-        const int total = p.n_tiles * 2 * p.m_tiles * p.k_iters;
-        const int base = total / grid, rem = total - base * grid;
-        r.it0 = b * base + min(b, rem);
-        r.it1 = r.it0 + base + (b < rem ? 1 : 0);
-    } else {
-        const int tiles = p.n_tiles * 2 * p.m_tiles;
+    const int tiles = p.n_tiles * 2 * p.m_tiles;
+    if (!p.streamk) {
+        if (part == 1) { r.it0 = r.it1 = 0; return r; }
         const int base = tiles / grid, rem = tiles - base * grid;
         const int t0 = b * base + min(b, rem);
         r.it0 = t0 * p.k_iters;
         r.it1 = (t0 + base + (b < rem ? 1 : 0)) * p.k_iters;
+        return r;
     }
+    if (part == 0) {
+        const int w = p.dp_tiles / grid;
+        r.it0 = b * w * p.k_iters;
+        r.it1 = (b + 1) * w * p.k_iters;
+        return r;
+    }
+    const int u0 = p.dp_tiles * p.k_iters;
+    const int total = (tiles - p.dp_tiles) * p.k_iters;
+    const int base = total / grid, rem = total - base * grid;
+    r.it0 = u0 + b * base + min(b, rem);
+    r.it1 = r.it0 + base + (b < rem ? 1 : 0);
     return r;
 }
+// which CTA's Stream-K share holds stage-unit `it` (it >= dp_tiles * k_iters)
 __device__ __forceinline__ int cta_of(const Params& p, int it, int grid) {
-    const int total = p.n_tiles * 2 * p.m_tiles * p.k_iters;
+    const int tiles = p.n_tiles * 2 * p.m_tiles;
+    const int u0 = p.dp_tiles * p.k_iters;
+    const int total = (tiles - p.dp_tiles) * p.k_iters;
     const int base = total / grid, rem = total - base * grid;
     const int thr = rem * (base + 1);
-    return it < thr ? it / (base + 1) : rem + (it - thr) / base;
+    const int x = it - u0;
+    return x < thr ? x / (base + 1) : rem + (x - thr) / base;
 }
 
 // two 16-byte quads (8 consecutive k-pairs) of row L -> fields 2*FP, 2*FP+1 x 8 TMEM columns, scaled
@@ -244,7 +261,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int grid = gridDim.x;
-    const Range rg = cta_range(p, blockIdx.x, grid);
+    const Range rg_parts[2] = {cta_part(p, blockIdx.x, grid, 0), cta_part(p, blockIdx.x, grid, 1)};
     const int spg_mask = (1 << p.gshift) - 1;
     const int S = p.stages;
 
@@ -279,40 +296,46 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 
     if (warp == kProducerWarp) {
         // =============================== TMA producer ===============================
-        if (rg.it1 > rg.it0) {
+        {
             const uint64_t pol_w = policy_evict_last();     // weight tiles are re-read by the other m-tiles
             const uint64_t pol_a = policy_evict_last();
-            const int n_it = rg.it1 - rg.it0;
-            int tile = rg.it0 / p.k_iters;
-            int k = rg.it0 - tile * p.k_iters;
-            TileCoord tc = tile_coord(p, tile);
             int stage = 0;
             uint32_t ephase = 1;
+            int n_total = 0;
             PPROF_DECL(pw_sc = 0, pw_empty = 0, pw_issue = 0);
             PPROF_T0(pt);
-            for (int i = 0; i < n_it; ++i) {
-                PPROF_ADD(pw_sc, pt);
-                wait(smem_u32(&ctl->empty[stage]), ephase, p, PSITE_EMPTY);
-                PPROF_ADD(pw_empty, pt);
-                if (elect_one()) {
-                    const uint32_t bar = smem_u32(&ctl->full[stage]);
-                    mbar_arrive_expect_tx(bar, kStageBytes);
-                    tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, tc.nt * 128, pol_w);
-                    tma_load_2d(ring + stage * kStageBytes + kWBytes, &tmap_a, bar, k * 64, tc.mt * kMb, pol_a);
-                }
-                __syncwarp();
-                PPROF_ADD(pw_issue, pt);
-                if (++stage == S) { stage = 0; ephase ^= 1u; }
-                if (++k == p.k_iters) {
-                    k = 0;
-                    tc = tile_coord(p, ++tile);
+            for (int part = 0; part < 2; ++part) {
+                const Range rg = rg_parts[part];
+                if (rg.it1 <= rg.it0) continue;
+                const int n_it = rg.it1 - rg.it0;
+                n_total += n_it;
+                int tile = rg.it0 / p.k_iters;
+                int k = rg.it0 - tile * p.k_iters;
+                TileCoord tc = tile_coord(p, tile);
+                for (int i = 0; i < n_it; ++i) {
+                    PPROF_ADD(pw_sc, pt);
+                    wait(smem_u32(&ctl->empty[stage]), ephase, p, PSITE_EMPTY);
+                    PPROF_ADD(pw_empty, pt);
+                    if (elect_one()) {
+                        const uint32_t bar = smem_u32(&ctl->full[stage]);
+                        mbar_arrive_expect_tx(bar, kStageBytes);
+                        tma_load_2d(ring + stage * kStageBytes, &tmap_w, bar, k * 64, tc.nt * 128, pol_w);
+                        tma_load_2d(ring + stage * kStageBytes + kWBytes, &tmap_a, bar, k * 64, tc.mt * kMb, pol_a);
+                    }
+                    __syncwarp();
+                    PPROF_ADD(pw_issue, pt);
+                    if (++stage == S) { stage = 0; ephase ^= 1u; }
+                    if (++k == p.k_iters) {
+                        k = 0;
+                        tc = tile_coord(p, ++tile);
+                    }
                 }
             }
-            if (lane == 0) { PPROF_OUT(8, pw_sc); PPROF_OUT(9, pw_empty); PPROF_OUT(10, pw_issue); PPROF_OUT(12, n_it); }
+            if (lane == 0) { PPROF_OUT(8, pw_sc); PPROF_OUT(9, pw_empty); PPROF_OUT(10, pw_issue); PPROF_OUT(12, n_total); }
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA issuer =================================
-        if (rg.it1 > rg.it0) {
+        {
             const uint32_t idesc = make_idesc_f16(BF16, 128, kMb);
             int stage = 0;
             int aslot = 0;
@@ -320,49 +343,54 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             int seg = 0;
             PPROF_DECL(mw_acc = 0, mw_afull = 0, mw_issue = 0);
             PPROF_T0(mt_);
-            for (int it = rg.it0; it < rg.it1;) {
-                const int tile = it / p.k_iters;
-                const int kb = it - tile * p.k_iters;
-                const int ke = min(p.k_iters, kb + (rg.it1 - it));
-                wait(smem_u32(&ctl->acc_empty), (uint32_t)(seg & 1) ^ 1u, p, PSITE_ACCEMPTY);
-                PPROF_ADD(mw_acc, mt_);
-                for (int k = kb; k < ke; ++k) {
-                    const uint64_t bdesc = make_smem_desc_sw128(ring + stage * kStageBytes + kWBytes);
-                    wait(smem_u32(&ctl->a_full[aslot]), aphase, p, PSITE_AFULL);
-                    PPROF_ADD(mw_afull, mt_);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_base = tmem + aslot * kACols;
-                        const uint32_t d_base = tmem + kDCol0;
-                        const uint32_t first = (k == kb) ? 0u : 1u;
+            for (int part = 0; part < 2; ++part) {
+                const Range rg = rg_parts[part];
+                for (int it = rg.it0; it < rg.it1;) {
+                    const int tile = it / p.k_iters;
+                    const int kb = it - tile * p.k_iters;
+                    const int ke = min(p.k_iters, kb + (rg.it1 - it));
+                    wait(smem_u32(&ctl->acc_empty), (uint32_t)(seg & 1) ^ 1u, p, PSITE_ACCEMPTY);
+                    PPROF_ADD(mw_acc, mt_);
+                    for (int k = kb; k < ke; ++k) {
+                        const uint64_t bdesc = make_smem_desc_sw128(ring + stage * kStageBytes + kWBytes);
+                        wait(smem_u32(&ctl->a_full[aslot]), aphase, p, PSITE_AFULL);
+                        PPROF_ADD(mw_afull, mt_);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_base = tmem + aslot * kACols;
+                            const uint32_t d_base = tmem + kDCol0;
+                            const uint32_t first = (k == kb) ? 0u : 1u;
 #pragma unroll
-                        for (int f = 0; f < NF; ++f) {
+                            for (int f = 0; f < NF; ++f) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                tc_mma_ts(d_base + f * kMb, a_base + f * 32 + kk * 8, bdesc + (uint64_t)((kk * 32) >> 4), idesc,
-                                          kk == 0 ? first : 1u);
+                                for (int kk = 0; kk < 4; ++kk)
+                                    tc_mma_ts(d_base + f * kMb, a_base + f * 32 + kk * 8, bdesc + (uint64_t)((kk * 32) >> 4), idesc,
+                                              kk == 0 ? first : 1u);
+                            }
+                            tc_commit(smem_u32(&ctl->empty[stage]));
+                            if (k == ke - 1) tc_commit(smem_u32(&ctl->acc_full));
                         }
-                        tc_commit(smem_u32(&ctl->empty[stage]));
-                        if (k == ke - 1) tc_commit(smem_u32(&ctl->acc_full));
+                        __syncwarp();
+                        if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
+                        if (++stage == S) stage = 0;
+                        PPROF_ADD(mw_issue, mt_);
                     }
-                    __syncwarp();
-                    if (++aslot == AS) { aslot = 0; aphase ^= 1u; }
-                    if (++stage == S) stage = 0;
-                    PPROF_ADD(mw_issue, mt_);
+                    it += ke - kb;
+                    ++seg;
                 }
-                it += ke - kb;
-                ++seg;
             }
             if (lane == 0) { PPROF_OUT(13, mw_acc); PPROF_OUT(14, mw_afull); PPROF_OUT(16, mw_issue); }
         }
     } else if (warp == kScaleWarp) {
         // =============================== scale blocks ===============================
-        if (rg.it1 > rg.it0) {
+        int nb = 0;
+        for (int part = 0; part < 2; ++part) {
+            const Range rg = rg_parts[part];
+            if (rg.it1 <= rg.it0) continue;
             const int n_it = rg.it1 - rg.it0;
             int tile = rg.it0 / p.k_iters;
             int k = rg.it0 - tile * p.k_iters;
             int nt = tile_coord(p, tile).nt;
-            int nb = 0;
             int last_blk = -1;
             for (int i = 0; i < n_it; ++i) {
                 const int blk = (k >> p.gshift) >> 3;
@@ -432,6 +460,8 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         int seg = 0;
         PPROF_DECL(dw_sc = 0, dw_full = 0, dw_aslot = 0, dw_piece = 0, dw_st = 0, dw_epiw = 0, dw_epi = 0);
         PPROF_T0(dt);
+        for (int part = 0; part < 2; ++part) {
+        const Range rg = rg_parts[part];
         for (int it = rg.it0; it < rg.it1;) {
             const int tile = it / p.k_iters;
             const int kb = it - tile * p.k_iters;
@@ -550,7 +580,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 #pragma unroll
                         for (int x = 0; x < 16; ++x) acc[x] = 0.f;
                         for (int c = first_cta; c <= last_cta; ++c) {
-                            const Range rc = cta_range(p, c, grid);
+                            const Range rc = cta_part(p, c, grid, 1);
                             const float* src = scratch + ((size_t)c * 2 + (rc.it0 >= tile_it0 ? 0 : 1)) * part_floats + my_off + mc;
 #pragma unroll
                             for (int x = 0; x < 16; x += 4) {
@@ -570,6 +600,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             PPROF_ADD(dw_epi, dt);
             it += ke - kb;
             ++seg;
+        }
         }
 #ifdef FB_PROFILE
         if (lane == 0 && (warp == 0 || warp == 9)) {
@@ -633,6 +664,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     // Stream-K needs one arrival counter per tile in the 64 KB counter region; beyond that (very large M x N, where
     // the last-wave loss is negligible anyway) every CTA takes whole tiles and no counter is touched.
     if ((size_t)tiles * 4 > kCounterBytes) p.streamk = 0;
+    p.dp_tiles = p.streamk ? (int)((tiles / grid) * grid) : 0;
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
 

@@ -599,3 +599,31 @@ def test_tune_and_pack_and_unpack(dev, flute):
     Q2, meta2 = tune.maybe_tune_and_repack(Q.to(dev), S, meta, example_batch_size=8)
     assert Q2.data_ptr() == Q.to(dev).data_ptr() or torch.equal(Q2.cpu(), Q.cpu())
     assert meta2.M == 8
+
+
+# ------------------------------------------------------------------------------------------------
+# FluteLinear / prepare_model_flute on the GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 1.5e-3), (torch.bfloat16, 1.0e-2)])
+@pytest.mark.parametrize("bits", [4, 3, 2])
+def test_flute_linear_matches_fake_quantised_model(dtype, tol, bits, dev):
+    """A small nn.Linear stack quantised by prepare_model_flute (NF, group 64; pack-time self check on) must match the
+    same stack with fake-quantised dense weights (nf_quantize_2: the kernel's arithmetic) -- the reference's model-level
+    check (tests/vllm.py:11-12,57-82: 1.5e-3 fp16 / 1.0e-2 bf16) -- for decode and prefill batch sizes."""
+    import copy
+    from flute_b200.integrations import FluteLinear, prepare_model_flute
+    torch.manual_seed(7)
+    K, H, N = 1024, 2048, 1024
+    dense = torch.nn.Sequential(torch.nn.Linear(K, H, bias=True), torch.nn.SiLU(), torch.nn.Linear(H, N, bias=False)).to(dev, dtype)
+    for p_ in dense.parameters():
+        p_.requires_grad_(False)
+        p_.mul_(0.5)
+    fake = copy.deepcopy(dense)
+    prepare_model_flute("fake", fake, bits, 64, fake=True)
+    prepare_model_flute("dense", dense, bits, 64, example_batch_size=1, check_correctness=True)
+    assert all(isinstance(dense[i], FluteLinear) for i in (0, 2))
+    for M in (1, 4, 40):
+        x = (torch.randn((M, K), device=dev) / 4).to(dtype)
+        y, y_ref = dense(x), fake(x)
+        e1, e2 = rel_errors(y, y_ref)
+        assert y.shape == (M, N) and e1 < tol and e2 < tol, (bits, dtype, M, e1, e2)
