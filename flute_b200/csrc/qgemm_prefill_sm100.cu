@@ -20,9 +20,10 @@
 //     scratch slot and summed by the last CTA to arrive: 16K atomics per partial tile cost ~40k cycles.
 //
 // Warp roles (608 threads, 1 CTA/SM, persistent):
-//   warps 0-15   dequantisers (2 quads of the row per warp), four TMEM A slots ahead of the MMAs; at the end of a
-//                tile the same warps run the epilogue: warp w owns field (w/4)&1, activation-row half w/8, lane
-//                quarter w%4
+//   warps 0-15   dequantisers: two sets of 8 (w/8) convert alternate 64-k stages, one stage apart -- 4 quads of the row
+//                per warp and turn, so the per-stage fixed cost (barrier probes, scale loads, loop) is paid once per 32
+//                look-ups instead of once per 16 -- four TMEM A slots ahead of the MMAs; at the end of a tile the same
+//                warps run the epilogue: warp w owns field (w/4)&1, activation-row half w/8, lane quarter w%4
 //   warp  16     TMA producer (weights + activations per stage)
 //   warp  17     tcgen05.mma issuer, TMEM allocator
 //   warp  18     scale blocks ([tile columns] x [8 groups]) by cp.async
@@ -65,6 +66,7 @@ constexpr uint32_t kScBytes = TN * 16;
 constexpr int AS = 4;                // TMEM A slots (NF * 32 = 64 columns each)
 constexpr uint32_t kACols = NF * 32;
 constexpr uint32_t kDCol0 = AS * kACols;
+constexpr int DQG = 2;               // dequantiser sets: 8 warps each, alternate stages (one stage apart)
 constexpr size_t kPartBytes = (size_t)NF * kMb * 128 * 4;   // one partial tile: fp32 [16 warps][32 lanes][64]
 
 struct Ctl {
@@ -124,6 +126,11 @@ __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const Params
             else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
         }
     }
+}
+// keep a kernel parameter in a register (ptxas otherwise re-reads the constant bank on every use)
+__device__ __forceinline__ int pin(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -192,9 +199,9 @@ __device__ __forceinline__ TileCoord tile_coord(const Params& p, int tile) {
     return c;
 }
 // Work of CTA b: part 0 = whole tiles, part 1 = its share of the Stream-K region (the tiles after dp_tiles, split at
-// stage granularity).  Whole tiles first keeps the split -- and its fix-up through global scratch -- to the remainder
-// that does not fill a wave: at 4096 x 4096, M = 4096 (512 tiles on 148 CTAs) 444 tiles need no fix-up and 68 are
-// shared by ~2 CTAs each, instead of every CTA boundary falling inside a tile.
+// stage granularity).  Whole tiles first keeps the split -- and its fix-up through global scratch -- to the last
+// wave-and-a-bit: at 4096 x 4096, M = 4096 (512 tiles on 148 CTAs) 296 tiles need no fix-up and 216 are split with
+// ~1.5 tiles of work per CTA, instead of every CTA boundary of the whole problem falling inside a tile.
 __device__ __forceinline__ Range cta_part(const Params& p, int b, int grid, int part) {
     Range r;
     const int tiles = p.n_tiles * 2 * p.m_tiles;
@@ -275,7 +282,7 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             mbar_init(smem_u32(&ctl->full[s]), 1);
             mbar_init(smem_u32(&ctl->empty[s]), 1);
         }
-        for (int s = 0; s < AS; ++s) mbar_init(smem_u32(&ctl->a_full[s]), kDqWarps);
+        for (int s = 0; s < AS; ++s) mbar_init(smem_u32(&ctl->a_full[s]), kDqWarps / DQG);
         mbar_init(smem_u32(&ctl->acc_full), 1);
         mbar_init(smem_u32(&ctl->acc_empty), kDqWarps);
         for (int s = 0; s < kScSlots; ++s) {
@@ -452,8 +459,12 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         const uint32_t nz = neg_zero2();
         const int ef = sw & 1, emh = sw >> 1;          // epilogue: field of the pair, activation-row half
 
+        const int set = sw >> 1;                // which stages (global stage parity) this warp converts
+        const int hw = sw & 1;                  // its quads of the row: 4*hw .. 4*hw + 3
+        const int r_gshift = pin(p.gshift), r_k_iters = pin(p.k_iters);
         int sc_idx = 0;
         uint32_t sc_par = 0;
+        int gs = 0;                             // stages since the CTA started (ring slot gs % S, A slot gs % AS)
         int stage = 0;
         uint32_t fphase = 0;
         int aslot = 0;
@@ -463,16 +474,17 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         for (int part = 0; part < 2; ++part) {
         const Range rg = rg_parts[part];
         for (int it = rg.it0; it < rg.it1;) {
-            const int tile = it / p.k_iters;
-            const int kb = it - tile * p.k_iters;
-            const int ke = min(p.k_iters, kb + (rg.it1 - it));
+            const int tile = it / r_k_iters;
+            const int kb = it - tile * r_k_iters;
+            const int ke = min(r_k_iters, kb + (rg.it1 - it));
             const TileCoord tc = tile_coord(p, tile);
             const int nl0 = n_local(L, 2 * tc.fp, p.tile_p), nl1 = n_local(L, 2 * tc.fp + 1, p.tile_p);
             int cur_blk = -1;
             int sc_g = -1;
             uint32_t sc[2] = {0, 0};
-            for (int k = kb; k < ke; ++k) {
-                const int g = k >> p.gshift;
+            for (int k = kb; k < ke; ++k, ++gs) {
+                const int g = k >> r_gshift;
+                // scale-block bookkeeping on EVERY stage (also the other set's): each block must be released by all 16 warps
                 if ((g >> 3) != cur_blk) {
                     if (cur_blk >= 0) {
                         __syncwarp();
@@ -482,31 +494,38 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                     cur_blk = g >> 3;
                     wait(smem_u32(&ctl->sc_full[sc_idx]), sc_par, p, PSITE_SCFULL);
                 }
-                if (g != sc_g) {
-                    const uint32_t sc_base = sc_smem + sc_idx * kScBytes + (g & 7) * 2;
-                    const uint32_t s0 = lds16(sc_base + nl0 * 16), s1 = lds16(sc_base + nl1 * 16);
-                    sc[0] = s0 | (s0 << 16);
-                    sc[1] = s1 | (s1 << 16);
-                    sc_g = g;
+                if ((gs & (DQG - 1)) == set) {
+                    if (g != sc_g) {
+                        const uint32_t sc_base = sc_smem + sc_idx * kScBytes + (g & 7) * 2;
+                        const uint32_t s0 = lds16(sc_base + nl0 * 16), s1 = lds16(sc_base + nl1 * 16);
+                        sc[0] = s0 | (s0 << 16);
+                        sc[1] = s1 | (s1 << 16);
+                        sc_g = g;
+                    }
+                    PPROF_ADD(dw_sc, dt);
+                    // (the stage's A slot is free as soon as its data has landed: with as many A slots as ring stages the
+                    // producer could only refill this stage after the MMAs that read slot `aslot` four stages ago completed)
+                    wait(smem_u32(&ctl->full[stage]), fphase, p, PSITE_FULL);
+                    PPROF_ADD(dw_full, dt);
+                    tc_fence_after();
+                    const uint32_t row = ring + stage * kStageBytes + wrow;
+                    const uint32_t tcol = tmem + lane_sel + aslot * kACols + hw * 16;
+                    if (tc.fp == 0) {
+                        piece<BF16, 0>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, sc, nz, tcol);
+                        piece<BF16, 0>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, sc, nz, tcol + 8);
+                    } else {
+                        piece<BF16, 1>(row, (4 * hw) ^ xq, (4 * hw + 1) ^ xq, lut, lane4, sc, nz, tcol);
+                        piece<BF16, 1>(row, (4 * hw + 2) ^ xq, (4 * hw + 3) ^ xq, lut, lane4, sc, nz, tcol + 8);
+                    }
+                    PPROF_ADD(dw_piece, dt);
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
+                    PPROF_ADD(dw_st, dt);
                 }
-                PPROF_ADD(dw_sc, dt);
-                // (the stage's A slot is free as soon as its data has landed: with as many A slots as ring stages the
-                // producer could only refill this stage after the MMAs that read slot `aslot` four stages ago completed)
-                wait(smem_u32(&ctl->full[stage]), fphase, p, PSITE_FULL);
-                PPROF_ADD(dw_full, dt);
-                tc_fence_after();
-                const uint32_t row = ring + stage * kStageBytes + wrow;
-                const uint32_t tcol = tmem + lane_sel + aslot * kACols + sw * 8;
-                if (tc.fp == 0) piece<BF16, 0>(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, sc, nz, tcol);
-                else piece<BF16, 1>(row, (2 * sw) ^ xq, (2 * sw + 1) ^ xq, lut, lane4, sc, nz, tcol);
-                PPROF_ADD(dw_piece, dt);
-                tc_wait_st();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&ctl->a_full[aslot]));
                 if (++aslot == AS) aslot = 0;
                 if (++stage == S) { stage = 0; fphase ^= 1u; }
-                PPROF_ADD(dw_st, dt);
             }
             if (cur_blk >= 0) {
                 __syncwarp();
@@ -664,7 +683,9 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     // Stream-K needs one arrival counter per tile in the 64 KB counter region; beyond that (very large M x N, where
     // the last-wave loss is negligible anyway) every CTA takes whole tiles and no counter is touched.
     if ((size_t)tiles * 4 > kCounterBytes) p.streamk = 0;
-    p.dp_tiles = p.streamk ? (int)((tiles / grid) * grid) : 0;
+    // data-parallel waves, then ONE Stream-K wave over the remainder plus a full wave's worth of tiles: every CTA's
+    // split share stays >= one tile of work and a tile has 2-3 contributors, not dozens
+    p.dp_tiles = (p.streamk && tiles / grid >= 2) ? (int)((tiles / grid - 1) * grid) : 0;
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
 

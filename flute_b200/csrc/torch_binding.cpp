@@ -78,21 +78,25 @@ at::Tensor qgemm_raw_simple(const at::Tensor& input, const at::Tensor& weight, c
                             const at::Tensor& table, const at::Tensor& table2, at::Tensor& workspace, int64_t num_bits,
                             int64_t group_size, int64_t template_id, int64_t num_sms) {
     (void)num_sms;   // accepted for signature compatibility; the engine sizes its grid from the device
+    // every argument check first: nothing below this block throws while a device guard or a half-built output is alive
     check_inputs(input, weight, scales, table, table2, workspace, num_bits, group_size);
-    const c10::cuda::OptionalCUDAGuard guard(input.device());
+    const int tile_p = tile_p_of(num_bits, template_id);
+    const int code = dtype_code(input);
+    const int flags = launch_flags();
     const int64_t K = input.size(-1), N = scales.size(0);
     at::Tensor x = input.reshape({-1, K});
     if (!x.is_contiguous()) x = x.contiguous();
     const int64_t M = x.size(0);
     at::Tensor out = at::empty({M, N}, input.options());
+    int rc = FLUTE_B200_OK;
     if (M > 0) {
-        const int rc = flute_b200_qgemm(x.data_ptr(), weight.data_ptr(), out.data_ptr(), scales.data_ptr(), table.data_ptr(),
-                                        table2.data_ptr(), workspace.data_ptr(), (size_t)workspace.numel(), (int)M, (int)N,
-                                        (int)K, (int)num_bits, (int)group_size, tile_p_of(num_bits, template_id),
-                                        dtype_code(input), launch_flags(), (int)input.get_device(),
-                                        at::cuda::getCurrentCUDAStream().stream());
-        TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
+        const c10::cuda::OptionalCUDAGuard guard(input.device());
+        rc = flute_b200_qgemm(x.data_ptr(), weight.data_ptr(), out.data_ptr(), scales.data_ptr(), table.data_ptr(),
+                              table2.data_ptr(), workspace.data_ptr(), (size_t)workspace.numel(), (int)M, (int)N, (int)K,
+                              (int)num_bits, (int)group_size, tile_p, code, flags, (int)input.get_device(),
+                              at::cuda::getCurrentCUDAStream(input.get_device()).stream());
     }
+    TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
     auto sizes = input.sizes().vec();
     sizes.back() = N;
     return out.reshape(sizes);
@@ -102,15 +106,16 @@ at::Tensor hadamard(const at::Tensor& x, int64_t hadamard_size) {
     TORCH_CHECK(x.scalar_type() == at::kHalf || x.scalar_type() == at::kBFloat16, "Only fp16 and bf16 supported currently");
     TORCH_CHECK(hadamard_size > 0 && x.size(-1) % hadamard_size == 0,
                 "flute_b200: last dimension must be a multiple of hadamard_size");
-    const c10::cuda::OptionalCUDAGuard guard(x.device());
+    const int code = dtype_code(x);
     at::Tensor xc = x.is_contiguous() ? x : x.contiguous();
     at::Tensor out = at::empty_like(xc);
+    int rc = FLUTE_B200_OK;
     if (xc.numel() > 0) {
-        const int rc = flute_b200_hadamard(xc.data_ptr(), out.data_ptr(), (long)(xc.numel() / hadamard_size),
-                                           (int)hadamard_size, dtype_code(x), (int)x.get_device(),
-                                           at::cuda::getCurrentCUDAStream().stream());
-        TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
+        const c10::cuda::OptionalCUDAGuard guard(x.device());
+        rc = flute_b200_hadamard(xc.data_ptr(), out.data_ptr(), (long)(xc.numel() / hadamard_size), (int)hadamard_size, code,
+                                 (int)x.get_device(), at::cuda::getCurrentCUDAStream(x.get_device()).stream());
     }
+    TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
     return out;
 }
 
