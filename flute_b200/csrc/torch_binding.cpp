@@ -12,6 +12,8 @@
 #include <torch/library.h>
 
 #include <atomic>
+#include <cstdarg>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -29,6 +31,22 @@ int env_flags() {
     return f;
 }
 
+// Error messages are formatted with snprintf and handed to TORCH_CHECK as ONE `const char*`, which selects
+// c10::detail::torchCheckFail(..., const char*).  The variadic form formats through a std::ostringstream instantiated in
+// THIS translation unit, and on the GPU boxes exactly those checks segfaulted inside the throw while single-literal
+// checks raised normally (gpurun r02h, tools/binding_errpath.py; same compiler and libstdc++ as the CPU container, where
+// both forms work -- the difference is the set of CUDA libraries resident in the process).  No iostreams here, then.
+[[noreturn]] void fail(const char* fmt, ...) {
+    static thread_local char buf[640];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    const char* msg = buf;
+    TORCH_CHECK(false, msg);
+    std::abort();   // not reached
+}
+
 int launch_flags() {
     int f = g_launch_flags.load(std::memory_order_relaxed);
     if (f < 0) {
@@ -42,22 +60,22 @@ int launch_flags() {
 // (3 SM multiples x 3 tile shapes {TileP 64, 32, 32} x 4 stage counts x {4 quant-map modes at 4 bits, else 1}).
 int tile_p_of(int64_t num_bits, int64_t template_id) {
     const int64_t per_tile = 4 * (num_bits == 4 ? 4 : 1);
-    TORCH_CHECK(template_id >= 0 && template_id < 9 * per_tile, "Unsupported template_id ", template_id,
-                " for num_bits ", num_bits);
+    if (!(template_id >= 0 && template_id < 9 * per_tile))
+        fail("Unsupported template_id %lld for num_bits %lld", (long long)template_id, (long long)num_bits);
     return ((template_id / per_tile) % 3) == 0 ? 64 : 32;
 }
 
 int dtype_code(const at::Tensor& t) {
     if (t.scalar_type() == at::kHalf) return FLUTE_B200_F16;
     if (t.scalar_type() == at::kBFloat16) return FLUTE_B200_BF16;
-    TORCH_CHECK(false, "flute_b200: unsupported dtype ", t.scalar_type(), " (fp16 / bf16 only)");
+    fail("flute_b200: unsupported dtype (fp16 / bf16 only), got scalar type %d", (int)t.scalar_type());
 }
 
 // The formal input contract of flute/ops.py:17-49, plus what the reference silently assumes (contiguity: it reads
 // raw data_ptr, qgemm.cpp:71).
 void check_inputs(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& scales, const at::Tensor& table,
                   const at::Tensor& table2, const at::Tensor& workspace, int64_t num_bits, int64_t group_size) {
-    TORCH_CHECK(num_bits == 2 || num_bits == 3 || num_bits == 4, "Unsupported `num_bits` ", num_bits);
+    if (!(num_bits == 2 || num_bits == 3 || num_bits == 4)) fail("Unsupported `num_bits` %lld", (long long)num_bits);
     TORCH_CHECK(input.dim() >= 2 && weight.dim() == 2 && scales.dim() == 2 && table.dim() == 1 && table2.dim() == 3 &&
                     workspace.dim() == 1, "flute_b200: bad tensor ranks");
     const auto dt = input.scalar_type();
@@ -96,7 +114,7 @@ at::Tensor qgemm_raw_simple(const at::Tensor& input, const at::Tensor& weight, c
                               (int)num_bits, (int)group_size, tile_p, code, flags, (int)input.get_device(),
                               at::cuda::getCurrentCUDAStream(input.get_device()).stream());
     }
-    TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
+    if (rc != FLUTE_B200_OK) fail("flute_b200: %s (code %d)", flute_b200_last_error(), rc);
     auto sizes = input.sizes().vec();
     sizes.back() = N;
     return out.reshape(sizes);
@@ -115,7 +133,7 @@ at::Tensor hadamard(const at::Tensor& x, int64_t hadamard_size) {
         rc = flute_b200_hadamard(xc.data_ptr(), out.data_ptr(), (long)(xc.numel() / hadamard_size), (int)hadamard_size, code,
                                  (int)x.get_device(), at::cuda::getCurrentCUDAStream(x.get_device()).stream());
     }
-    TORCH_CHECK(rc == FLUTE_B200_OK, "flute_b200: ", flute_b200_last_error(), " (code ", rc, ")");
+    if (rc != FLUTE_B200_OK) fail("flute_b200: %s (code %d)", flute_b200_last_error(), rc);
     return out;
 }
 
