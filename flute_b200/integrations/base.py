@@ -103,7 +103,9 @@ def prepare_model_flute(name: str, module: torch.nn.Module, num_bits: int, group
                 continue
             dtype, device = child.weight.dtype, child.weight.device
             custom = None if custom_scales_dict is None else custom_scales_dict[full]
-            _, idx, scales, qmap = nf_utils.nf_quantize(child.weight.float(), num_bits, group_size, custom_scales=custom)
+            # (on the weight in its OWN dtype, like the reference, integrations/base.py:133-137: code indices then agree
+            # with nf_quantize_2's, whose fp16 / bf16 arithmetic decides values next to a pivot differently from fp32)
+            _, idx, scales, qmap = nf_utils.nf_quantize(child.weight, num_bits, group_size, custom_scales=custom)
             if int(idx.max()) >= 2 ** num_bits:
                 raise ValueError(f"{full}: code index out of range")
             W_idx = idx.to(torch.uint8).T.contiguous()                    # [K, N] code indices

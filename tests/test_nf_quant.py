@@ -73,7 +73,7 @@ def test_prepare_model_flute_module_contract(bits, group):
     W_hat = flute_oracle.dequantize(lin.weight.numpy(), lin.scales.numpy(),
                                     lin.tables2.numpy(), bits, group, "float16")                   # [K, N] uint16 bits
     W_hat = torch.from_numpy(W_hat.view(np.int16)).view(torch.float16)
-    _, idx, absmax, values = nf_utils.nf_quantize(W0.float(), bits, group)
+    _, idx, absmax, values = nf_utils.nf_quantize(W0, bits, group)
     expect = (values.to(torch.float16)[idx] * absmax.to(torch.float16).view(N, K // group).repeat_interleave(group, 1))
     assert torch.equal(W_hat.T.contiguous().view(torch.int16), expect.contiguous().view(torch.int16))
     # state dict round trip into a freshly constructed module (meta-free path the HF loader uses)
