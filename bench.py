@@ -396,17 +396,19 @@ def run_own(args):
     tpx = None
     if tp > 1:
         progress("tensor-parallel exchange: symmetric memory rendezvous")
-        tpx = parallel.FusedGather(dev, rank, tp, [(name, M, N, LAYERS) for name, N, K in SHAPES], torch.bfloat16)
+        tpx = parallel.FusedGather(dev, rank, tp, [(name, M, N, LAYERS, 1 if name == "down" else 0) for name, N, K in SHAPES],
+                                   torch.bfloat16)
     bufs = {name: torch.empty((M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
     gathered = {name: torch.empty((tp, M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
 
-    def linear_cabi(x, lin, name, mode):
+    def linear_cabi(x, lin, name, mode, last=False):
         """mode: 'fused' (epilogue writes every peer's gathered buffer), 'none' (no exchange: local slice only),
         'nccl' (all_gather_into_tensor after the GEMM)."""
         Q, S, n_loc, K = lin[name]
         launches[0] += 1
         if tp > 1 and mode == "fused":
-            return tpx.qgemm(x, Q, S, table, table2, ws, name, n_loc, K, BITS, GROUP, flags)
+            # arrival counters only where something other than the next qgemm reads the buffer: the step's final output
+            return tpx.qgemm(x, Q, S, table, table2, ws, name, n_loc, K, BITS, GROUP, flags, signal_counter=last)
         out = bufs[name]
         rc = _lib.lib.flute_b200_qgemm(x.data_ptr(), Q.data_ptr(), out.data_ptr(), S.data_ptr(), table.data_ptr(),
                                        table2.data_ptr(), ws.data_ptr(), ws.numel(), M, n_loc, K, BITS, GROUP, 32,
@@ -418,7 +420,7 @@ def run_own(args):
             return gathered[name].view(M, -1)
         return out
 
-    def linear_api(x, lin, name, mode):
+    def linear_api(x, lin, name, mode, last=False):
         Q, S, n_loc, K = lin[name]
         out = flute_b200.qgemm_simple(x, Q, S, table, table2, ws, BITS, GROUP)
         if tp > 1:
@@ -428,11 +430,11 @@ def run_own(args):
     def token(x, linear, mode="fused"):
         if tp > 1 and mode == "fused":
             tpx.begin_step()
-        for lin in layers:
+        for li, lin in enumerate(layers):
             qkv = linear(x, lin, "qkv", mode)
             o = linear(qkv[:, :4096], lin, "o", mode)
             gu = linear(o, lin, "gate_up", mode)
-            x = linear(gu[:, :14336], lin, "down", mode)
+            x = linear(gu[:, :14336], lin, "down", mode, last=(li == len(layers) - 1))
         if tp > 1 and mode == "fused":
             tpx.end_step("down")
         return x

@@ -48,7 +48,9 @@ _u = ctypes.c_uint
 class TpDesc(ctypes.Structure):
     """`flute_b200_tp` of include/flute_b200.h (tensor-parallel fused exchange descriptor)."""
     _fields_ = [("tp", _i), ("rank", _i), ("n_total", _i), ("out_peers", _vp * 8), ("flag_peers", _vp * 8),
-                ("in_flag", _vp), ("in_per_step", _u), ("in_offset", _u), ("epoch", _vp)]
+                ("in_flag", _vp), ("in_per_step", _u), ("in_offset", _u), ("epoch", _vp),
+                ("ll_peers", _vp * 8), ("out_uses", _u), ("out_call", _u), ("in_ll", _vp), ("in_ll_stride", _i),
+                ("in_uses", _u), ("in_call", _u), ("signal_counter", _i)]
 
 
 

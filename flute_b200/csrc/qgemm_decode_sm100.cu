@@ -143,6 +143,16 @@ struct DecodeParams {
     unsigned in_per_step;         // arrivals on in_flag per step; expected = (epoch - 1) * in_per_step + in_offset
     unsigned in_offset;
     const unsigned* epoch;        // device word: step number (>= 1)
+    // Low-latency hand-over between two qgemm launches (the NCCL "LL" idea): next to the plain buffer every output
+    // element is also stored as ONE 8-byte word {value, sequence number}; an aligned 8-byte store is single-copy atomic,
+    // so a reader that sees the expected sequence number has the value -- no fence, no separate flag, one NVLink
+    // one-way trip.  sequence = (epoch - 1) * uses + call + 1 (grows for ever; the buffers start zeroed).
+    uint2* ll_peers[8];           // every rank's LL image of this output, [M, n_total] uint2 (nullptr: not kept)
+    unsigned out_uses, out_call;
+    const uint2* in_ll;           // LL image A is read from (nullptr: plain A through cp.async)
+    int in_ll_stride;             // elements per row of that image
+    unsigned in_uses, in_call;
+    int signal_counter;           // also bump the arrival counters (needed only when something other than a qgemm_tp reads D)
 };
 
 enum : int { DSITE_FULL = 21, DSITE_AEMPTY, DSITE_PFULL, DSITE_SCFULL, DSITE_EMPTY, DSITE_SCEMPTY, DSITE_AFULL, DSITE_PEMPTY };
@@ -433,18 +443,28 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         return *reinterpret_cast<volatile uint32_t*>(&ctl->tmem_base);
     };
 
-    // D[m, n] = v -- locally, or (tensor parallel) into every rank's gathered buffer at this rank's column offset
-    auto store_out = [&](int m, int n, uint16_t v) {
+    // D[m, n] = v -- locally, or (tensor parallel) into every rank's gathered buffer at this rank's column offset, plain
+    // and as a {value, sequence} word for the low-latency readers
+    auto store_out = [&](int m, int n, uint16_t v, unsigned seq) {
         if (p.tp <= 1) {
             p.D[(size_t)m * p.N + n] = v;
         } else {
             const size_t off = (size_t)m * p.n_total + (size_t)p.rank * p.N + n;
 #pragma unroll 1
-            for (int r = 0; r < p.tp; ++r) p.out_peers[r][off] = v;
+            for (int r = 0; r < p.tp; ++r) {
+                p.out_peers[r][off] = v;
+                if (p.ll_peers[r] != nullptr)
+                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p.ll_peers[r] + off), "r"((uint32_t)v), "r"(seq) : "memory");
+            }
         }
     };
-    // after a tile's stores (made visible system-wide by the callers' fences): one arrival on every rank's counter
+    auto out_sequence = [&]() -> unsigned {
+        return (p.tp > 1) ? (ld_acquire_sys_u32(p.epoch) - 1u) * p.out_uses + p.out_call + 1u : 0u;
+    };
+    // after a tile's stores (made visible system-wide by ONE fence of the signalling thread, which the CTA-level barrier
+    // before it makes cumulative over the other threads' stores): one arrival on every rank's counter
     auto signal_tile = [&]() {
+        __threadfence_system();
 #pragma unroll 1
         for (int r = 0; r < p.tp; ++r) red_release_sys_add_u32(p.flag_peers[r], 1u);
     };
@@ -657,6 +677,40 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
+            if (p.in_ll != nullptr) {
+                // Low-latency path (tensor parallel): A is read from the {value, sequence} image of a gathered buffer.  Lane l
+                // owns k-pair l of the stage: one 16-byte volatile load = two words; it spins until both carry this
+                // hand-over's sequence number, then writes the pair into the swizzled tile.  No cp.async, no look-ahead:
+                // the words arrive from the peers while the dequantisers are already filling TMEM.
+                const unsigned expected = (ld_acquire_sys_u32(p.epoch) - 1u) * p.in_uses + p.in_call + 1u;
+                for (int i = 0; i < n_it; ++i) {
+                    if (!kScaleWarpExists) scale_step(tile, k, nb, last_blk);
+                    wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
+                    const uint32_t bt = ring + stage * kStageBytes + kWBytes;
+                    for (int r = 0; r < p.M; ++r) {
+                        const uint2* src = p.in_ll + (size_t)r * p.in_ll_stride + (size_t)k * 64 + 2 * lane;
+                        uint32_t d0, f0, d1, f1;
+                        uint64_t t0 = 0;
+                        uint32_t spins = 0;
+                        for (;;) {
+                            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
+                            if (f0 == expected && f1 == expected) break;
+                            if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
+                                const uint64_t now = globaltimer_ns();
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, f0, expected, -4);
+                            }
+                        }
+                        const uint32_t dst = bt + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                        sts32(dst, (d0 & 0xffffu) | (d1 << 16));
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&ctl->act_full[stage]));
+                    if (++stage == p.stages) { stage = 0; ephase ^= 1u; }
+                    if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
+                }
+            } else {
             const int r0 = lane >> 3, c16 = lane & 7;          // this lane's row (mod 4) and 16-byte chunk
             const uint8_t* a_lane = reinterpret_cast<const uint8_t*>(p.A) + c16 * 16;
             for (int i = 0; i < n_it; ++i) {
@@ -691,6 +745,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             for (int i = max(0, n_it - D); i < n_it; ++i) {
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->act_full[astage]));
                 if (++astage == p.stages) astage = 0;
+            }
             }
         }
     } else if (kScaleWarpExists && warp == kScaleWarp) {
@@ -739,6 +794,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | last | (contributors << 20));
                     }
                     if (last) {
+                        const unsigned seq = out_sequence();
                         __threadfence();      // every lane: order its reads after lane 0's acquire
                         float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
                         const int n_base = tile * TN;
@@ -755,11 +811,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                                 for (int qq = 0; qq < 4; ++qq) {
                                     accum[(j * kMb + m) * 128 + qq * 32 + lane] = 0.f;
                                     const int n = n_base + n_local<BITS, NJ>(qq * 32 + lane, j, p.tile_p);
-                                    if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]));
+                                    if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]), seq);
                                 }
                         }
-                        if (p.tp > 1) {
-                            __threadfence_system();
+                        if (p.tp > 1 && p.signal_counter) {
                             __syncwarp();
                             if (lane == 0) signal_tile();
                         }
@@ -868,17 +923,17 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             const bool full_k = (kb == 0) && (ke == p.k_iters);
             const int n_base = tile * TN;
             if (full_k) {
+                const unsigned seq = out_sequence();
 #pragma unroll
                 for (int j = 0; j < NFA; ++j) {
                     const int n = n_base + nloc[j];
                     if (n < p.N) {
 #pragma unroll
                         for (int m = 0; m < MC; ++m)
-                            if (m < p.M) store_out(m, n, f32_to_t<BF16>(acc[j][m]));
+                            if (m < p.M) store_out(m, n, f32_to_t<BF16>(acc[j][m]), seq);
                     }
                 }
-                if (p.tp > 1) {      // whole tile written by the apply warps: one arrival per rank once all of them are done
-                    __threadfence_system();
+                if (p.tp > 1 && p.signal_counter) {   // whole tile written by the apply warps: one arrival per rank once all are done
                     asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
                     if (warp == kApplyWarp0 && lane == 0) signal_tile();
                 }
@@ -1051,6 +1106,12 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
         }
         p.in_flag = a.tp->in_flag; p.in_per_step = a.tp->in_per_step; p.in_offset = a.tp->in_offset;
         p.epoch = a.tp->epoch;
+        for (int r = 0; r < p.tp; ++r) p.ll_peers[r] = static_cast<uint2*>(a.tp->ll_peers[r]);
+        p.out_uses = a.tp->out_uses; p.out_call = a.tp->out_call;
+        p.in_ll = static_cast<const uint2*>(a.tp->in_ll); p.in_ll_stride = a.tp->in_ll_stride;
+        p.in_uses = a.tp->in_uses; p.in_call = a.tp->in_call;
+        p.signal_counter = a.tp->signal_counter;
+        if (p.in_ll != nullptr && ((reinterpret_cast<uintptr_t>(p.in_ll) & 15) != 0 || (p.in_ll_stride & 1) != 0)) return FB_ERR_SHAPE;
     }
 
     const uint32_t fixed = F::SC_SLOTS * TN * 16 + F::LUTB + sizeof(Ctl) + 1024 /*alignment slack*/;

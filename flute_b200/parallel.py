@@ -63,6 +63,7 @@ class FusedGather:
     synchronise on the host, so a whole token step captures into one CUDA graph.
 
         fg = FusedGather(dev, rank, tp, [("qkv", 1, 6144, 32), ...], torch.bfloat16)   # name, M, N_total, uses per step
+                                                                      # [, uses per step that also bump the counters]
         fg.begin_step();  y = fg.qgemm(x, Q_r, S_r, table, table2, ws, "qkv", n_loc, K, 4, 64, flags);  ...;  fg.end_step("down")
 
     Every rank must issue the same sequence of calls per step; each named buffer is written `uses` times per step.
@@ -76,10 +77,13 @@ class FusedGather:
         self.device, self.rank, self.tp, self.dtype, self.num_bits = device, rank, tp, dtype, num_bits
         group = group if group is not None else dist.group.WORLD
         flag_bytes = 128 * len(outputs)
-        offs, off = {}, flag_bytes
-        for name, M, n_total, uses in outputs:
+        offs, ll_offs, off = {}, {}, flag_bytes
+        outputs = [tuple(o) + ((o[3],) if len(o) == 4 else ()) for o in outputs]     # signalled uses default to all uses
+        for name, M, n_total, uses, signalled in outputs:
             offs[name] = off
             off += (M * n_total * 2 + 255) // 256 * 256
+            ll_offs[name] = off                      # {value, sequence} image: 8 bytes per element
+            off += (M * n_total * 8 + 255) // 256 * 256
         self.buf = symm_mem.empty(off, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group)
@@ -88,45 +92,63 @@ class FusedGather:
         dist.barrier(group)                      # every rank's counters are zero before anyone's first store can land
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.out: Dict[str, dict] = {}
-        for i, (name, M, n_total, uses) in enumerate(outputs):
+        for i, (name, M, n_total, uses, signalled) in enumerate(outputs):
             n_loc = n_total // tp
             arrivals = tp * _lib.lib.flute_b200_tp_tiles(n_loc, num_bits)
             view = self.buf[offs[name]:offs[name] + M * n_total * 2].view(dtype).view(M, n_total)
-            self.out[name] = dict(M=M, n_total=n_total, uses=uses, arrivals=arrivals, view=view,
+            self.out[name] = dict(M=M, n_total=n_total, uses=uses, signalled_uses=signalled, signalled=0, arrivals=arrivals, view=view,
                                   base=ptrs[rank] + offs[name], nbytes=M * n_total * 2,
                                   out_peers=[p + offs[name] for p in ptrs], flag_peers=[p + 128 * i for p in ptrs],
-                                  calls=0)
+                                  ll_base=ptrs[rank] + ll_offs[name], ll_peers=[p + ll_offs[name] for p in ptrs], calls=0)
 
     def begin_step(self) -> None:
         for o in self.out.values():
             o["calls"] = 0
+            o["signalled"] = 0
         st = torch.cuda.current_stream(self.device).cuda_stream
         self._lib.check(self._lib.lib.flute_b200_tp_advance(self.epoch.data_ptr(), self.device.index, st))
 
-    def _guard_of(self, x: torch.Tensor):
-        """(flag pointer, arrivals per step, arrivals needed) of the gathered buffer `x` lives in, or (None, 0, 0)."""
+    def _source_of(self, x: torch.Tensor):
+        """The gathered buffer `x` lives in (None: a local tensor) and x's element offset inside it."""
         p = x.data_ptr()
         for o in self.out.values():
             if o["base"] <= p < o["base"] + o["nbytes"]:
-                return o["flag_peers"][self.rank], o["uses"] * o["arrivals"], o["calls"] * o["arrivals"]
-        return None, 0, 0
+                return o, (p - o["base"]) // 2
+        return None, 0
 
     def qgemm(self, x: torch.Tensor, Q: torch.Tensor, S: torch.Tensor, table: torch.Tensor, table2: torch.Tensor,
               workspace: torch.Tensor, name: str, n_loc: int, K: int, num_bits: int, group_size: int, flags: int,
-              tile_P: int = 32) -> torch.Tensor:
+              tile_P: int = 32, signal_counter: Optional[bool] = None) -> torch.Tensor:
+        """`signal_counter=False` skips the arrival counters of this output: valid when every reader of it is another
+        `qgemm` of this object (they take the low-latency word image); `end_step` needs the counters of its buffer."""
         _lib = self._lib
         o = self.out[name]
         M = x.shape[0]
-        if M != o["M"] or n_loc * self.tp != o["n_total"] or not x.is_contiguous():
+        if M != o["M"] or n_loc * self.tp != o["n_total"] or x.stride(-1) != 1:
             raise ValueError("flute_b200: FusedGather.qgemm shape mismatch")
         d = _lib.TpDesc()
         d.tp, d.rank, d.n_total = self.tp, self.rank, o["n_total"]
         for r in range(self.tp):
             d.out_peers[r] = o["out_peers"][r]
             d.flag_peers[r] = o["flag_peers"][r]
-        flag, per_step, offset = self._guard_of(x)
-        d.in_flag = flag
-        d.in_per_step, d.in_offset = per_step, offset
+        for r in range(self.tp):
+            d.ll_peers[r] = o["ll_peers"][r]
+        d.out_uses, d.out_call = o["uses"], o["calls"]
+        if signal_counter is None:
+            signal_counter = o["signalled_uses"] == o["uses"]
+        d.signal_counter = 1 if signal_counter else 0
+        src, elem_off = self._source_of(x)
+        if src is None and not x.is_contiguous():
+            raise ValueError("flute_b200: local activations must be contiguous")
+        if src is not None:
+            if src["calls"] < 1:
+                raise ValueError("flute_b200: FusedGather.qgemm reads a gathered buffer that was not written in this step")
+            if x.stride(0) != src["n_total"] and M > 1:
+                raise ValueError("flute_b200: activations must be rows of the gathered buffer")
+            d.in_ll = src["ll_base"] + 8 * elem_off          # the low-latency image of the same elements
+            d.in_ll_stride = src["n_total"]
+            d.in_uses, d.in_call = src["uses"], src["calls"] - 1
+            d.in_flag = None                                  # (the sequence numbers are the guard)
         d.epoch = self.epoch.data_ptr()
         code = _lib.BF16 if self.dtype == torch.bfloat16 else _lib.F16
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -135,12 +157,15 @@ class FusedGather:
                                           code, flags, self.device.index, st, ctypes.byref(d))
         _lib.check(rc)
         o["calls"] += 1
+        o["signalled"] += 1 if signal_counter else 0
         return o["view"]
 
     def end_step(self, name: str) -> None:
         """Stream-ordered wait for the last write of `name` in this step (before a non-flute consumer reads it)."""
         o = self.out[name]
         st = torch.cuda.current_stream(self.device).cuda_stream
-        rc = self._lib.lib.flute_b200_tp_wait(o["flag_peers"][self.rank], o["uses"] * o["arrivals"], o["calls"] * o["arrivals"],
+        if o["signalled"] < 1:
+            raise ValueError(f"flute_b200: no call of this step bumped the counters of `{name}`")
+        rc = self._lib.lib.flute_b200_tp_wait(o["flag_peers"][self.rank], o["signalled_uses"] * o["arrivals"], o["signalled"] * o["arrivals"],
                                               self.epoch.data_ptr(), self.device.index, st)
         self._lib.check(rc)

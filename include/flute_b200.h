@@ -150,6 +150,18 @@ typedef struct flute_b200_tp {
     unsigned in_per_step;
     unsigned in_offset;
     const unsigned* epoch;       /* device word holding the step number */
+    /* Low-latency hand-over between two qgemm_tp calls: besides the plain buffer every output element is also stored as
+     * one 8-byte word {value, sequence number} into ll_peers[r] ([M, n_total] such words on every rank; NULL = not kept).
+     * A consumer call given `in_ll` (the word image of the buffer its A lives in, at A's first element; row stride
+     * in_ll_stride words) reads A from there and spins per word on the sequence number -- no fence, no counter: one
+     * NVLink one-way trip.  sequence = (*epoch - 1) * uses + call + 1 with `uses` = producing calls per step of that
+     * buffer and `call` = index of the producing call within the step (out_* for this call's output, in_* for A). */
+    void* ll_peers[8];
+    unsigned out_uses, out_call;
+    const void* in_ll;
+    int in_ll_stride;
+    unsigned in_uses, in_call;
+    int signal_counter;          /* 0: skip the arrival counters (every reader of D is a qgemm_tp call using in_ll) */
 } flute_b200_tp;
 
 FLUTE_B200_API int flute_b200_qgemm_tp(const void* A, const void* Q, const void* S, const void* table, const void* table2,

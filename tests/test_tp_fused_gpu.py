@@ -13,14 +13,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("M", [1, 3])
-def test_tp_fused_exchange_matches_single_gpu(M):
+@pytest.mark.parametrize("M,counters", [(1, 0), (3, 0), (2, 1)])
+def test_tp_fused_exchange_matches_single_gpu(M, counters):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs on this node")
     world = 8 if n >= 8 else 4 if n >= 4 else 2
-    env = dict(os.environ, TP_TEST_M=str(M))
-    port = 29700 + (os.getpid() % 200) + M
+    env = dict(os.environ, TP_TEST_M=str(M), TP_TEST_COUNTERS=str(counters))
+    port = 29700 + (os.getpid() % 200) + M + 7 * counters
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "tp_fused_worker.py")]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
