@@ -12,8 +12,8 @@ tok/s here is "linears only", the quantity SURVEY.md section 8(d) defines.
 N > 1 (torchrun): tensor parallel, every linear column-sharded N/tp per rank (SURVEY.md section 8e);
 strong scaling (one token stream).  The exchange step is fused into the GEMM: the epilogue stores
 its [1, N/tp] slice straight into every peer's gathered activation buffer over NVLink (symmetric
-memory) and bumps an arrival counter there; the next linear's activation warp waits on its own
-counter.  `tp` in the JSON line reports the step with that exchange, without any exchange, and with
+memory), each element as one 8-byte {value, sequence number} word; the next linear's activation
+warp reads those words and spins on the sequence number (flute_b200/parallel.py::FusedGather).  `tp` in the JSON line reports the step with that exchange, without any exchange, and with
 NCCL all-gathers instead.
 
 Keys beyond the base contract: `roofline` (achieved HBM GB/s of the qGEMM kernel vs the measured
@@ -490,8 +490,9 @@ def run_own(args):
         ms_none = timed(g_none.replay, args.steps, 3)
         progress("tp: step with NCCL all-gathers (eager)")
         ms_nccl = timed(lambda: token(x0, linear_cabi, "nccl"), max(5, args.steps // 5), 2)
-        tp_record = {"exchange": "fused into the GEMM epilogue: NVLink peer stores into symmetric memory + arrival counters, "
-                                 "consumer's activation warp waits (no collective kernel)",
+        tp_record = {"exchange": "fused into the GEMM epilogue: NVLink peer stores of {value, sequence} words into every rank's "
+                                 "symmetric-memory buffer; the consuming launch's activation warp spins on the sequence "
+                                 "numbers (no fence, no collective kernel); arrival counters only for the step's final output",
                      "tok_s_fused_exchange": tok_s, "tok_s_without_exchange": 1e3 / ms_none,
                      "tok_s_nccl_allgather_eager": 1e3 / ms_nccl,
                      "bytes_exchanged_per_rank_per_step": LAYERS * sum(M * N // tp * 2 * (tp - 1) for _, N, K in SHAPES)}
