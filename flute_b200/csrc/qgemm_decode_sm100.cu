@@ -452,7 +452,9 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             const size_t off = (size_t)m * p.n_total + (size_t)p.rank * p.N + n;
 #pragma unroll 1
             for (int r = 0; r < p.tp; ++r) {
-                p.out_peers[r][off] = v;
+                // the plain image is for readers outside this engine; calls whose output only feeds other qgemm_tp calls
+                // (signal_counter == 0) keep just the word image and halve their NVLink stores
+                if (p.signal_counter || p.ll_peers[r] == nullptr) p.out_peers[r][off] = v;
                 if (p.ll_peers[r] != nullptr)
                     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p.ll_peers[r] + off), "r"((uint32_t)v), "r"(seq) : "memory");
             }

@@ -119,8 +119,9 @@ class FusedGather:
     def qgemm(self, x: torch.Tensor, Q: torch.Tensor, S: torch.Tensor, table: torch.Tensor, table2: torch.Tensor,
               workspace: torch.Tensor, name: str, n_loc: int, K: int, num_bits: int, group_size: int, flags: int,
               tile_P: int = 32, signal_counter: Optional[bool] = None) -> torch.Tensor:
-        """`signal_counter=False` skips the arrival counters of this output: valid when every reader of it is another
-        `qgemm` of this object (they take the low-latency word image); `end_step` needs the counters of its buffer."""
+        """`signal_counter=False`: every reader of this output is another `qgemm` of this object (they take the
+        low-latency word image), so neither the arrival counters nor the plain image are written -- the returned view
+        is then only a handle for the next `qgemm`, not data; `end_step` needs a signalled call of its buffer."""
         _lib = self._lib
         o = self.out[name]
         M = x.shape[0]

@@ -161,7 +161,8 @@ typedef struct flute_b200_tp {
     const void* in_ll;
     int in_ll_stride;
     unsigned in_uses, in_call;
-    int signal_counter;          /* 0: skip the arrival counters (every reader of D is a qgemm_tp call using in_ll) */
+    int signal_counter;          /* 0: every reader of D is a qgemm_tp call using in_ll: skip the arrival counters AND the
+                                  * plain [M, n_total] image (only the word image is written) */
 } flute_b200_tp;
 
 FLUTE_B200_API int flute_b200_qgemm_tp(const void* A, const void* Q, const void* S, const void* table, const void* table2,
