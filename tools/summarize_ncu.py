@@ -53,6 +53,7 @@ def summarise(rep, title, f):
                 i = hdr.index(k)
                 f.write(f"  {k:95s} {r[i]:>16s} {units[i]}\n")
                 d[k] = r[i]
+                d[k + '__unit'] = units[i]
         res.append(d)
     h, kernels = source(rep)
     if h:
@@ -109,7 +110,22 @@ if os.path.exists(lp):
 vals = []
 for d in dec:
     try:
-        rd = float(d["dram__bytes_read.sum"]); wr = float(d["dram__bytes_write.sum"])
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = float(d["dram__bytes_read.sum"]) * scale[d["dram__bytes_read.sum__unit"]]
+        wr = float(d["dram__bytes_write.sum"]) * scale[d["dram__bytes_write.sum__unit"]]
         vals.append((rd, wr))
     except Exception:
         pass
+if vals:
+    # algorithmic bytes of the same launches (bench.py shapes, in launch order qkv, o, gate_up, down), for the ratio
+    sys.path.insert(0, ROOT)
+    import bench
+    algo = [bench.algorithmic_bytes(1, N, K) for _, N, K in bench.SHAPES][:len(vals)]
+    out = {"source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, {len(vals)} decode launches of bench.py "
+                     f"(second eager token: qkv, o, gate_up, down)",
+           "dram_bytes_per_launch": [rd + wr for rd, wr in vals],
+           "algorithmic_bytes_per_launch": algo,
+           "dram_bytes_per_launch_avg": sum(rd + wr for rd, wr in vals) / len(vals),
+           "ratio_dram_over_algorithmic": sum(rd + wr for rd, wr in vals) / max(1, sum(algo))}
+    with open(os.path.join(out_dir, f"{tag}_traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
