@@ -30,19 +30,16 @@
 // running CTA then has ~1.5 weight tiles in flight and streams at 1.6 TB/s instead of 3.2 (gpurun r02a/r02b,
 // DESIGN.md section 3.1).  What a launch can hide behind its predecessor is done inside this footprint instead:
 // weights, scales and the LUT never wait for the previous kernel (static weights), the dequantisers fill all three
-// TMEM A slots before the activations exist, and the split-K hand-over costs no global-memory round trip on the
-// contributors' side: a partial tile leaves its CTA as 8-byte {value, 1} words in a per-CTA slot; the tile's owner (the
-// CTA holding the tile's first stages, for which that segment comes last) polls the words, adds them in CTA order --
-// results are bit-reproducible -- zeroes the slot and writes the tile.  (Round 1 / early round 2: red.global.add.f32 +
-// arrival counter + last-arriver read-back, 2.4 us after the last stage on the critical path, r02d.)
+// TMEM A slots before the activations exist, and the split-K fix-up runs in its own warp off the streaming path.
 //
 // Warp roles (persistent over a contiguous Stream-K range of (tile, k) stages).  DQ = dequantiser warps
-// (16); 800 threads for M <= 4, 896 for the opt-in 5 <= M <= 16 variant:
+// (16); 832 threads for M <= 4, 928 for the opt-in 5 <= M <= 16 variant:
 //   warps 0..DQ-1    dequantisers: warp w owns TMEM lane quarter w%4 and a fixed set of 16-byte quads of its row
 //   warp DQ          TMA producer (packed weights, one 128-row x 64-k box per stage; optional L2 prefetch ahead)
 //   warps DQ+1,DQ+3  tcgen05.mma issuers (alternate scale groups; warp DQ+1 also allocates TMEM)
 //   warp DQ+2        activation rows of every stage (16-byte cp.async, up to three stages ahead)
-//   warps DQ+4..     4 (8 for M > 4) scale application (acc += S * P_g), epilogue and split-K hand-over (below)
+//   warps DQ+4..     4 (8 for M > 4) scale application (acc += S * P_g), epilogue and split-K fix-up
+//   next warp        split-K fix-up: arrival counter, last-arriver conversion of the fp32 partial sums to D
 //   last warp        scale blocks (cp.async); for M > 4 the activation warp does this
 #include "ptx.cuh"
 #include "qgemm_sm100.h"
@@ -86,9 +83,9 @@ struct DCfg<2> {
 __host__ __device__ constexpr int apply_warps(int mc) { return mc > 4 ? 8 : 4; }
 // M <= 4: one more warp copies the scale blocks; with 8 apply warps the activation warp does
 __host__ __device__ constexpr bool has_scale_warp(int mc) { return mc <= 4; }
-// dequantisers + producer, 2 MMA issuers, activation warp + apply warps (+ scale warp)
+// dequantisers + producer, 2 MMA issuers, activation warp + apply warps + fix-up warp (+ scale warp)
 __host__ __device__ constexpr int threads_for(int dq, int mc) {
-    return (dq + 4 + apply_warps(mc) + (has_scale_warp(mc) ? 1 : 0)) * 32;
+    return (dq + 4 + apply_warps(mc) + 1 + (has_scale_warp(mc) ? 1 : 0)) * 32;
 }
 constexpr uint32_t kSmemBudget = 232448u;
 constexpr int kMaxStagesAny = 10;
@@ -109,6 +106,7 @@ struct Ctl {
     uint64_t sc_full[kMaxScSlots];
     uint64_t sc_empty[kMaxScSlots];
     uint64_t tmem_ready;     // the allocating warp arrives once the TMEM base address is in tmem_base
+    uint64_t fix_full[2];    // partial-tile hand-over apply warps -> fix-up warp (a contiguous range has <= 2 partial segments)
     uint32_t tmem_base;
 };
 
@@ -361,7 +359,8 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     constexpr uint32_t kPCols = NJ * kMb;
     constexpr int kApplyWarps = apply_warps(MC);
     constexpr bool kScaleWarpExists = has_scale_warp(MC);
-    constexpr int kScaleWarp = kApplyWarp0 + kApplyWarps;   // exists iff kScaleWarpExists
+    constexpr int kFixWarp = kApplyWarp0 + kApplyWarps;     // split-K fix-up, off the streaming path
+    constexpr int kScaleWarp = kFixWarp + 1;                // exists iff kScaleWarpExists
     constexpr int NFA = NJ / (kApplyWarps / 4);   // fields per apply warp
     static_assert(kPCol0 + PS * kPCols <= (uint32_t)F::TMEM_COLS, "TMEM budget");
     static_assert((kApplyWarp0 & 3) == 0, "apply warp w must own TMEM lane quarter w & 3");
@@ -422,6 +421,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             mbar_init(smem_u32(&ctl->sc_empty[s]), kApplyWarps);
         }
         mbar_init(smem_u32(&ctl->tmem_ready), 1);
+        for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&ctl->fix_full[s]), kApplyWarps);
         mbar_fence_init();
     }
     // First sync: barriers visible.  The producer starts streaming right after it, the dequant warps build the LUT;
@@ -762,6 +762,70 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 if (++k == p.k_iters) { k = 0; ++tile; last_blk = -1; }
             }
         }
+    } else if (warp == kFixWarp) {
+        // =============================== split-K fix-up ==============================
+        // For every partial segment of this CTA's range, in order: once the apply warps have issued their reductions,
+        // bump the tile's arrival counter (release: their red.adds happen-before it through the mbarrier hand-over);
+        // the CTA that arrives last reads the completed fp32 sums back, zeroes the scratch (workspace contract:
+        // zero between launches) and writes the tile in T.  A contiguous Stream-K range has at most two partial
+        // segments (its first and its last tile), one mbarrier each.
+        if (rg.it1 > rg.it0) {
+            int n_fix = 0;
+            bool synced = false;
+            for (int it = rg.it0; it < rg.it1;) {
+                const int tile = it / p.k_iters;
+                const int kb = it - tile * p.k_iters;
+                const int ke = min(p.k_iters, kb + (rg.it1 - it));
+                if (!((kb == 0) && (ke == p.k_iters))) {
+                    wait(smem_u32(&ctl->fix_full[n_fix]), 0u, p, DSITE_PFULL, 2);
+                    ++n_fix;
+                    if (!synced) { pdl_wait_prior_grids(); synced = true; }
+                    if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
+                    const int tile_it0 = tile * p.k_iters;
+                    const int first_cta = cta_of(total, tile_it0, grid);
+                    const int contributors = cta_of(total, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
+                    int last = 0;
+                    if (lane == 0) {
+                        const int old = atom_add_acq_rel(reinterpret_cast<int*>(p.workspace) + tile, 1);
+                        last = (old == contributors - 1) ? 1 : 0;
+                        if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
+                    }
+                    last = __shfl_sync(0xffffffffu, last, 0);
+                    if (p.trace != nullptr && lane == 0) {
+                        p.trace[blockIdx.x * 48 + 45] = globaltimer_ns();
+                        p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | last | (contributors << 20));
+                    }
+                    if (last) {
+                        const unsigned seq = out_sequence();
+                        __threadfence();      // every lane: order its reads after lane 0's acquire
+                        float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
+                        const int n_base = tile * TN;
+#pragma unroll 1
+                        for (int m = 0; m < p.M; ++m) {
+                            float v[NJ][4];
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) v[j][qq] = __ldcg(accum + (j * kMb + m) * 128 + qq * 32 + lane);
+#pragma unroll
+                            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) {
+                                    accum[(j * kMb + m) * 128 + qq * 32 + lane] = 0.f;
+                                    const int n = n_base + n_local<BITS, NJ>(qq * 32 + lane, j, p.tile_p);
+                                    if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]), seq);
+                                }
+                        }
+                        if (p.tp > 1 && p.signal_counter) {
+                            __syncwarp();
+                            if (lane == 0) signal_tile();
+                        }
+                    }
+                    if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
+                }
+                it += ke - kb;
+            }
+        }
     } else if (warp >= kApplyWarp0) {
         // ===================== scale + accumulate + epilogue ========================
         const int q = warp & 3;
@@ -779,6 +843,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         int sc_idx = 0;
         uint32_t sc_par = 0;
         bool synced = false;
+        int n_fix = 0;                     // partial segments handed to the fix-up warp so far (<= 2)
         DPROF_DECL(aw_pfull = 0, aw_sc = 0, aw_work = 0, aw_epi = 0);
         DPROF_T0(at);
         for (int it = rg.it0; it < rg.it1;) {
@@ -874,83 +939,19 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
                     if (warp == kApplyWarp0 && lane == 0) signal_tile();
                 }
-            } else if (kb > 0) {
-                // Partial K range that does not start the tile: this CTA is a CONTRIBUTOR.  Its fp32 partial sums go out
-                // as 8-byte {value, 1} words (an aligned 8-byte store is single-copy atomic: whoever sees the 1 has the
-                // value) into this CTA's slot -- a contiguous Stream-K range has at most one such segment, its first --
-                // and the warps carry on: no reduction, no fence, no counter, nothing to wait for.
-                uint2* slot = reinterpret_cast<uint2*>(p.workspace + p.partial_offset) + (size_t)blockIdx.x * (NJ * kMb * 128);
+            } else {
+                // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left zero
+                // on exit), then hand over to the fix-up warp (arrival counter, last-arriver conversion) and carry on
+                // with the next segment: nothing on the streaming path waits for a global-memory round trip.
+                float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
 #pragma unroll
                 for (int j = 0; j < NFA; ++j)
 #pragma unroll
                     for (int m = 0; m < MC; ++m)
-                        if (m < p.M)
-                            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + ((fset * NFA + j) * kMb + m) * 128 + L),
-                                         "r"(__float_as_uint(acc[j][m])), "r"(1u) : "memory");
-            } else {
-                // Partial K range that starts the tile: this CTA is the tile's OWNER, and the segment is the last thing it
-                // does (ranges are contiguous: the tile's first stages sit at the end of the owner's range, the rest at the
-                // start / whole of the following CTAs' ranges, which therefore finish no later).  Add the contributors' words
-                // in CTA order (deterministic), hand each slot back zeroed (workspace contract), write the tile.
-                const int tile_it0 = tile * p.k_iters;
-                const int last_cta = cta_of(total, tile_it0 + p.k_iters - 1, grid);
-                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
-#pragma unroll 1
-                for (int c = blockIdx.x + 1; c <= last_cta; ++c) {
-                    uint2* slot = reinterpret_cast<uint2*>(p.workspace + p.partial_offset) + (size_t)c * (NJ * kMb * 128);
-                    uint32_t val[NFA][MC];
-                    uint32_t pending = 0;
-#pragma unroll
-                    for (int j = 0; j < NFA; ++j)
-#pragma unroll
-                        for (int m = 0; m < MC; ++m) pending |= (m < p.M) ? (1u << (j * MC + m)) : 0u;
-                    uint64_t t0 = 0;
-                    uint32_t spins = 0;
-                    while (pending != 0) {
-#pragma unroll
-                        for (int j = 0; j < NFA; ++j)
-#pragma unroll
-                            for (int m = 0; m < MC; ++m)
-                                if (pending & (1u << (j * MC + m))) {
-                                    uint32_t v, f;
-                                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f)
-                                                 : "l"(slot + ((fset * NFA + j) * kMb + m) * 128 + L) : "memory");
-                                    if (f != 0u) { val[j][m] = v; pending &= ~(1u << (j * MC + m)); }
-                                }
-                        if (pending != 0 && (++spins & 0xff) == 0 && p.timeout_ns != 0) {
-                            const uint64_t now = globaltimer_ns();
-                            if (t0 == 0) t0 = now;
-                            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_PFULL, (uint32_t)c, pending, -5);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < NFA; ++j)
-#pragma unroll
-                        for (int m = 0; m < MC; ++m)
-                            if (m < p.M) {
-                                acc[j][m] += __uint_as_float(val[j][m]);
-                                asm volatile("st.global.v2.u32 [%0], {%1, %1};" ::"l"(slot + ((fset * NFA + j) * kMb + m) * 128 + L), "r"(0u) : "memory");
-                            }
-                }
-                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) {
-                    p.trace[blockIdx.x * 48 + 45] = globaltimer_ns();
-                    p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | 1 | ((last_cta - (int)blockIdx.x + 1) << 20));
-                }
-                const unsigned seq = out_sequence();
-#pragma unroll
-                for (int j = 0; j < NFA; ++j) {
-                    const int n = n_base + nloc[j];
-                    if (n < p.N) {
-#pragma unroll
-                        for (int m = 0; m < MC; ++m)
-                            if (m < p.M) store_out(m, n, f32_to_t<BF16>(acc[j][m]), seq);
-                    }
-                }
-                if (p.tp > 1 && p.signal_counter) {
-                    asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
-                    if (warp == kApplyWarp0 && lane == 0) signal_tile();
-                }
-                if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
+                        if (m < p.M) red_add_f32(accum + ((fset * NFA + j) * kMb + m) * 128 + L, acc[j][m]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&ctl->fix_full[n_fix]));
+                ++n_fix;
             }
             if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 5] = globaltimer_ns();
             DPROF_ADD(aw_epi, at);
@@ -1139,9 +1140,8 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
     constexpr size_t kCounterBytes = 65536;
     p.partial_offset = (uint32_t)kCounterBytes;
-    // split-K slots: one per CTA, NJ x 16 x 128 eight-byte words, zero between launches (the owner hands them back zeroed)
-    const size_t need = kCounterBytes + (size_t)grid * F::NJ * kMb * 128 * 8;
-    if (need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
+    const size_t need = kCounterBytes + (size_t)p.n_tiles * F::NJ * kMb * 128 * 4;
+    if ((size_t)p.n_tiles * 4 > kCounterBytes || need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
 
     CUtensorMap tm_w;
     const uint64_t P = (uint64_t)a.N / 16 * BITS;
