@@ -94,6 +94,11 @@ template <bool BF16>
 __global__ void __launch_bounds__(256) hadamard_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                        long rows, int h, int log_h, int rows_per_block, float scale) {
     extern __shared__ float buf[];
+    // Launched with programmatic stream serialisation: it may start while the producer of `in` is still running, so it
+    // waits for that first -- and releases its own dependents at once: a qgemm that follows (flute.qgemm_hadamard) is
+    // then resident, with its weights streaming and its TMEM slots filling, while these few CTAs transform the row.
+    pdl_wait_prior_grids();
+    pdl_launch_dependents();
     const long row0 = (long)blockIdx.x * rows_per_block;
     const int nrows = (int)min((long)rows_per_block, rows - row0);
     if (nrows <= 0) return;
@@ -129,12 +134,21 @@ int hadamard_launch(const void* in, void* out, long rows, int h, int bf16, cudaS
     const float scale = 1.0f / sqrtf((float)h);
     const uint16_t* i16 = static_cast<const uint16_t*>(in);
     uint16_t* o16 = static_cast<uint16_t*>(out);
-    if (bf16) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(hadamard_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        hadamard_kernel<true><<<(unsigned)blocks, 256, smem, stream>>>(i16, o16, rows, h, log_h, rpb, scale);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(hadamard_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        hadamard_kernel<false><<<(unsigned)blocks, 256, smem, stream>>>(i16, o16, rows, h, log_h, rpb, scale);
+    auto kern = bf16 ? hadamard_kernel<true> : hadamard_kernel<false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, i16, o16, rows, h, log_h, rpb, scale) != cudaSuccess) {
+        cudaGetLastError();
+        return FB_ERR_LAUNCH;
     }
     if (cudaGetLastError() != cudaSuccess) return FB_ERR_LAUNCH;
     return FB_OK;

@@ -627,3 +627,33 @@ def test_flute_linear_matches_fake_quantised_model(dtype, tol, bits, dev):
         y, y_ref = dense(x), fake(x)
         e1, e2 = rel_errors(y, y_ref)
         assert y.shape == (M, N) and e1 < tol and e2 < tol, (bits, dtype, M, e1, e2)
+
+
+@pytest.mark.parametrize("h", [128, 512, 2048])
+def test_hadamard_rounding_vs_fp16_accumulating_reference(h, dev):
+    """The reference's fp16 Hadamard accumulates IN fp16 between its tensor-core passes (hadamard_transform_cuda.cu:55-59)
+    and holds no test; this engine does the butterflies in fp32 and rounds once.  Pin what that means: against the
+    exact (fp64) transform our fp16 result is within one rounding (<= 2^-11 relative per element, plus the input's
+    own rounding), and an emulation of the reference's scheme (round to fp16 after every butterfly pass) sits at least as
+    far from the exact result as ours -- so a caller switching engines sees the same or smaller error, never a larger one."""
+    from flute_b200 import ops
+    torch.manual_seed(h)
+    x = torch.randn((5, 2 * h), device=dev).to(torch.float16)
+    ours = ops.hadamard_transform(x, h).double()
+    xr = x.double().reshape(-1, h)
+    H = torch.ones((1, 1), dtype=torch.float64, device=dev)
+    while H.shape[0] < h:
+        H = torch.cat([torch.cat([H, H], 1), torch.cat([H, -H], 1)], 0)         # Sylvester order
+    exact = (xr @ H / h ** 0.5).reshape(5, 2 * h)
+    emu = x.reshape(-1, h).clone()
+    s = 1
+    while s < h:                                                                 # fp16 after every pass
+        e = emu.float().reshape(-1, h // (2 * s), 2, s)
+        emu = torch.stack([e[:, :, 0] + e[:, :, 1], e[:, :, 0] - e[:, :, 1]], 2).reshape(-1, h).to(torch.float16)
+        s *= 2
+    emu = (emu.float() / h ** 0.5).to(torch.float16).double().reshape(5, 2 * h)
+    err_ours = (ours - exact).abs().max().item()
+    err_emu = (emu - exact).abs().max().item()
+    scale = exact.abs().max().item()
+    assert err_ours <= scale * 2.0 ** -10, (h, err_ours, scale)
+    assert err_ours <= err_emu * 1.01 + 1e-12, (h, err_ours, err_emu)
