@@ -12,6 +12,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libflute_b200_prof.so" if os.environ.get("FLUTE_B200_PROFILE") == "1"
                         else "libflute_b200.so")   # _prof: per-role cycle counters, tools/microbench.py only
+if os.environ.get("FLUTE_B200_LIB"):                # tools only: A/B an older build of the same C ABI on one box
+    LIB_PATH = os.path.join(_HERE, os.environ["FLUTE_B200_LIB"])
 
 # every symbol include/flute_b200.h declares
 EXPORTS = (

@@ -131,6 +131,12 @@ struct DecodeParams {
     int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
     int l2_prefetch;     // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
     uint32_t partial_offset;
+};
+
+// Tensor-parallel extension of the parameters: a separate kernel argument that only the TP instantiation carries, so the
+// single-GPU kernel's parameter block, code and registers are exactly what they are without it (folding these fields into
+// DecodeParams cost every tp = 1 launch 0.7 us: gpurun r02ab, same box, 9.12 / 8.14 / 17.97 / 12.00 -> 9.86 / 8.92 / 19.00 / 12.63 us).
+struct TpParams {
     // Tensor-parallel column shard with the exchange fused in (tp > 1): the tile writer stores its [M, tile] slice into
     // EVERY rank's gathered buffer (peer-mapped pointers, NVLink) at column offset rank * N, then bumps that buffer's
     // arrival counter on every rank (release, system scope); the activation warp of the consuming launch waits on its
@@ -144,8 +150,8 @@ struct DecodeParams {
     unsigned in_offset;
     const unsigned* epoch;        // device word: step number (>= 1)
     // Low-latency hand-over between two qgemm launches (the NCCL "LL" idea): next to the plain buffer every output
-    // element is also stored as ONE 8-byte word {value, sequence number}; an aligned 8-byte store is single-copy atomic,
-    // so a reader that sees the expected sequence number has the value -- no fence, no separate flag, one NVLink
+    // element is also stored as ONE 8-byte word {value, sequence number} -- an aligned 8-byte store is single-copy atomic,
+    // so a reader that sees the expected sequence number has the value: no fence, no separate flag, one NVLink
     // one-way trip.  sequence = (epoch - 1) * uses + call + 1 (grows for ever; the buffers start zeroed).
     uint2* ll_peers[8];           // every rank's LL image of this output, [M, n_total] uint2 (nullptr: not kept)
     unsigned out_uses, out_call;
@@ -154,6 +160,12 @@ struct DecodeParams {
     unsigned in_uses, in_call;
     int signal_counter;           // also bump the arrival counters (needed only when something other than a qgemm_tp reads D)
 };
+template <bool TP>
+struct TpArg {
+    TpParams v;
+};
+template <>
+struct TpArg<false> {};
 
 enum : int { DSITE_FULL = 21, DSITE_AEMPTY, DSITE_PFULL, DSITE_SCFULL, DSITE_EMPTY, DSITE_SCEMPTY, DSITE_AFULL, DSITE_PEMPTY };
 
@@ -339,9 +351,9 @@ __device__ __forceinline__ float scale_to_f32(uint32_t s16) {
     else return __half2float(__ushort_as_half((unsigned short)s16));
 }
 
-template <int BITS, bool BF16, int MC>
+template <int BITS, bool BF16, int MC, bool TP>
 __global__ void __launch_bounds__(threads_for(DCfg<BITS>::DQ, MC), 1)
-qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodeParams p) {
+qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodeParams p, const TpArg<TP> tpa) {
     using F = DCfg<BITS>;
     constexpr int NJ = F::NJ, CK2 = F::CK2, CPS = F::CPS;
     constexpr int AS = F::A_SLOTS, PS = F::P_SLOTS;
@@ -446,29 +458,57 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     // D[m, n] = v -- locally, or (tensor parallel) into every rank's gathered buffer at this rank's column offset, plain
     // and as a {value, sequence} word for the low-latency readers
     auto store_out = [&](int m, int n, uint16_t v, unsigned seq) {
-        if (p.tp <= 1) {
+        if constexpr (!TP) {
             p.D[(size_t)m * p.N + n] = v;
         } else {
-            const size_t off = (size_t)m * p.n_total + (size_t)p.rank * p.N + n;
+            const TpParams& t = tpa.v;
+            const size_t off = (size_t)m * t.n_total + (size_t)t.rank * p.N + n;
 #pragma unroll 1
-            for (int r = 0; r < p.tp; ++r) {
+            for (int r = 0; r < t.tp; ++r) {
                 // the plain image is for readers outside this engine; calls whose output only feeds other qgemm_tp calls
                 // (signal_counter == 0) keep just the word image and halve their NVLink stores
-                if (p.signal_counter || p.ll_peers[r] == nullptr) p.out_peers[r][off] = v;
-                if (p.ll_peers[r] != nullptr)
-                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p.ll_peers[r] + off), "r"((uint32_t)v), "r"(seq) : "memory");
+                if (t.signal_counter || t.ll_peers[r] == nullptr) t.out_peers[r][off] = v;
+                if (t.ll_peers[r] != nullptr)
+                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(t.ll_peers[r] + off), "r"((uint32_t)v), "r"(seq) : "memory");
             }
         }
     };
     auto out_sequence = [&]() -> unsigned {
-        return (p.tp > 1) ? (ld_acquire_sys_u32(p.epoch) - 1u) * p.out_uses + p.out_call + 1u : 0u;
+        if constexpr (TP) return (ld_acquire_sys_u32(tpa.v.epoch) - 1u) * tpa.v.out_uses + tpa.v.out_call + 1u;
+        else return 0u;
     };
     // after a tile's stores (made visible system-wide by ONE fence of the signalling thread, which the CTA-level barrier
     // before it makes cumulative over the other threads' stores): one arrival on every rank's counter
     auto signal_tile = [&]() {
-        __threadfence_system();
+        if constexpr (TP) {
+            __threadfence_system();
 #pragma unroll 1
-        for (int r = 0; r < p.tp; ++r) red_release_sys_add_u32(p.flag_peers[r], 1u);
+            for (int r = 0; r < tpa.v.tp; ++r) red_release_sys_add_u32(tpa.v.flag_peers[r], 1u);
+        }
+    };
+    auto tp_signals = [&]() -> bool {
+        if constexpr (TP) return tpa.v.signal_counter != 0;
+        else return false;
+    };
+    auto tp_in_flag = [&]() -> const unsigned* {
+        if constexpr (TP) return tpa.v.in_flag;
+        else return nullptr;
+    };
+    auto tp_expected_arrivals = [&]() -> unsigned {
+        if constexpr (TP) return (ld_acquire_sys_u32(tpa.v.epoch) - 1u) * tpa.v.in_per_step + tpa.v.in_offset;
+        else return 0u;
+    };
+    auto tp_in_ll = [&]() -> const uint2* {
+        if constexpr (TP) return tpa.v.in_ll;
+        else return nullptr;
+    };
+    auto tp_in_ll_stride = [&]() -> int {
+        if constexpr (TP) return tpa.v.in_ll_stride;
+        else return 0;
+    };
+    auto tp_expected_sequence = [&]() -> unsigned {
+        if constexpr (TP) return (ld_acquire_sys_u32(tpa.v.epoch) - 1u) * tpa.v.in_uses + tpa.v.in_call + 1u;
+        else return 0u;
     };
 
     // One step of the scale-block schedule (called once per stage, in stage order, by ONE warp): when stage (tile, k)
@@ -660,13 +700,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             // the wait for the previous kernel.
             if (!kScaleWarpExists && p.static_weights) scale_step(tile, k, nb, last_blk);
             if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
-            if (p.in_flag != nullptr) {
+            if (TP && tp_in_flag() != nullptr) {
                 // tensor parallel: A is a gathered buffer; every rank's slice must have arrived (acquire, system scope)
                 if (lane == 0) {
-                    const unsigned expected = (ld_acquire_sys_u32(p.epoch) - 1u) * p.in_per_step + p.in_offset;
+                    const unsigned expected = tp_expected_arrivals();
                     uint64_t t0 = 0;
                     uint32_t spins = 0;
-                    while ((int)(ld_acquire_sys_u32(p.in_flag) - expected) < 0) {
+                    while ((int)(ld_acquire_sys_u32(tp_in_flag()) - expected) < 0) {
                         if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
                             const uint64_t now = globaltimer_ns();
                             if (t0 == 0) t0 = now;
@@ -679,18 +719,18 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
-            if (p.in_ll != nullptr) {
+            if (TP && tp_in_ll() != nullptr) {
                 // Low-latency path (tensor parallel): A is read from the {value, sequence} image of a gathered buffer.  Lane l
                 // owns k-pair l of the stage: one 16-byte volatile load = two words; it spins until both carry this
                 // hand-over's sequence number, then writes the pair into the swizzled tile.  No cp.async, no look-ahead:
                 // the words arrive from the peers while the dequantisers are already filling TMEM.
-                const unsigned expected = (ld_acquire_sys_u32(p.epoch) - 1u) * p.in_uses + p.in_call + 1u;
+                const unsigned expected = tp_expected_sequence();
                 for (int i = 0; i < n_it; ++i) {
                     if (!kScaleWarpExists) scale_step(tile, k, nb, last_blk);
                     wait(smem_u32(&ctl->empty[stage]), ephase, p, DSITE_EMPTY);
                     const uint32_t bt = ring + stage * kStageBytes + kWBytes;
                     for (int r = 0; r < p.M; ++r) {
-                        const uint2* src = p.in_ll + (size_t)r * p.in_ll_stride + (size_t)k * 64 + 2 * lane;
+                        const uint2* src = tp_in_ll() + (size_t)r * tp_in_ll_stride() + (size_t)k * 64 + 2 * lane;
                         uint32_t d0, f0, d1, f1;
                         uint64_t t0 = 0;
                         uint32_t spins = 0;
@@ -816,7 +856,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                                     if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]), seq);
                                 }
                         }
-                        if (p.tp > 1 && p.signal_counter) {
+                        if (tp_signals()) {
                             __syncwarp();
                             if (lane == 0) signal_tile();
                         }
@@ -935,7 +975,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                             if (m < p.M) store_out(m, n, f32_to_t<BF16>(acc[j][m]), seq);
                     }
                 }
-                if (p.tp > 1 && p.signal_counter) {   // whole tile written by the apply warps: one arrival per rank once all are done
+                if (tp_signals()) {   // whole tile written by the apply warps: one arrival per rank once all are done
                     asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
                     if (warp == kApplyWarp0 && lane == 0) signal_tile();
                 }
@@ -1072,7 +1112,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     }
 }
 
-template <int BITS, bool BF16, int MC>
+template <int BITS, bool BF16, int MC, bool TP>
 static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     using F = DCfg<BITS>;
     constexpr int TN = F::NJ * 128;
@@ -1097,23 +1137,25 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.ablate = a.ablate;
     p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
     p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : 0;
-    if (a.tp != nullptr && a.tp->tp > 1) {
+    TpArg<TP> tpa{};
+    if constexpr (TP) {
+        TpParams& t = tpa.v;
         if (a.tp->tp > 8 || a.tp->rank < 0 || a.tp->rank >= a.tp->tp || a.tp->n_total != a.tp->tp * a.N || a.tp->epoch == nullptr)
             return FB_ERR_SHAPE;
-        p.tp = a.tp->tp; p.rank = a.tp->rank; p.n_total = a.tp->n_total;
-        for (int r = 0; r < p.tp; ++r) {
+        t.tp = a.tp->tp; t.rank = a.tp->rank; t.n_total = a.tp->n_total;
+        for (int r = 0; r < t.tp; ++r) {
             if (a.tp->out_peers[r] == nullptr || a.tp->flag_peers[r] == nullptr) return FB_ERR_NULL;
-            p.out_peers[r] = static_cast<uint16_t*>(a.tp->out_peers[r]);
-            p.flag_peers[r] = a.tp->flag_peers[r];
+            t.out_peers[r] = static_cast<uint16_t*>(a.tp->out_peers[r]);
+            t.flag_peers[r] = a.tp->flag_peers[r];
+            t.ll_peers[r] = static_cast<uint2*>(a.tp->ll_peers[r]);
         }
-        p.in_flag = a.tp->in_flag; p.in_per_step = a.tp->in_per_step; p.in_offset = a.tp->in_offset;
-        p.epoch = a.tp->epoch;
-        for (int r = 0; r < p.tp; ++r) p.ll_peers[r] = static_cast<uint2*>(a.tp->ll_peers[r]);
-        p.out_uses = a.tp->out_uses; p.out_call = a.tp->out_call;
-        p.in_ll = static_cast<const uint2*>(a.tp->in_ll); p.in_ll_stride = a.tp->in_ll_stride;
-        p.in_uses = a.tp->in_uses; p.in_call = a.tp->in_call;
-        p.signal_counter = a.tp->signal_counter;
-        if (p.in_ll != nullptr && ((reinterpret_cast<uintptr_t>(p.in_ll) & 15) != 0 || (p.in_ll_stride & 1) != 0)) return FB_ERR_SHAPE;
+        t.in_flag = a.tp->in_flag; t.in_per_step = a.tp->in_per_step; t.in_offset = a.tp->in_offset;
+        t.epoch = a.tp->epoch;
+        t.out_uses = a.tp->out_uses; t.out_call = a.tp->out_call;
+        t.in_ll = static_cast<const uint2*>(a.tp->in_ll); t.in_ll_stride = a.tp->in_ll_stride;
+        t.in_uses = a.tp->in_uses; t.in_call = a.tp->in_call;
+        t.signal_counter = a.tp->signal_counter;
+        if (t.in_ll != nullptr && ((reinterpret_cast<uintptr_t>(t.in_ll) & 15) != 0 || (t.in_ll_stride & 1) != 0)) return FB_ERR_SHAPE;
     }
 
     const uint32_t fixed = F::SC_SLOTS * TN * 16 + F::LUTB + sizeof(Ctl) + 1024 /*alignment slack*/;
@@ -1148,7 +1190,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     int rc = make_tmap_2d(&tm_w, CU_TENSOR_MAP_DATA_TYPE_UINT16, a.Q, (uint64_t)a.K, P, (uint64_t)a.K * 2, 64, 128,
                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FB_OK) return rc;
-    auto kern = qgemm_decode_kernel<BITS, BF16, MC>;
+    auto kern = qgemm_decode_kernel<BITS, BF16, MC, TP>;
     static PerDeviceOnce attr_set;      // one per template instantiation
     if (!attr_set.done(a.device)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess) {
@@ -1171,7 +1213,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     }
     cfg.attrs = attrs;
     cfg.numAttrs = nattr;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_w, p, tpa);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return FB_ERR_LAUNCH;
@@ -1181,9 +1223,14 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
 template <int BITS, bool BF16>
 static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
-    if (a.M == 1) return launch_t<BITS, BF16, 1>(a, stream);
-    if (a.M <= 4) return launch_t<BITS, BF16, 4>(a, stream);
-    if constexpr (BITS == 4) return launch_t<BITS, BF16, 16>(a, stream);
+    if (a.tp != nullptr && a.tp->tp > 1) {        // tensor-parallel fused exchange: its own instantiations (M <= 4)
+        if (a.M == 1) return launch_t<BITS, BF16, 1, true>(a, stream);
+        if (a.M <= 4) return launch_t<BITS, BF16, 4, true>(a, stream);
+        return FB_ERR_SHAPE;
+    }
+    if (a.M == 1) return launch_t<BITS, BF16, 1, false>(a, stream);
+    if (a.M <= 4) return launch_t<BITS, BF16, 4, false>(a, stream);
+    if constexpr (BITS == 4) return launch_t<BITS, BF16, 16, false>(a, stream);
     return FB_ERR_INTERNAL;
 }
 
