@@ -110,6 +110,9 @@ struct Ctl {
     uint32_t tmem_base;
 };
 
+// Kept small on purpose: together with the 128-byte tensor map the kernel's parameter block stays under 256 bytes.  Its
+// size is a measurable per-launch cost on this part (gpurun r02ab / r02ab2, same box: 159 bytes less = 0.75-1.1 us less
+// per launch at every shape), so small integers are bytes, derived values (G, P, the scratch offset) are recomputed.
 struct DecodeParams {
     const uint16_t* A;
     const uint8_t* Q;      // packed weights [P, K] int16 (also behind the tensor map; raw pointer for the entry prefetch)
@@ -119,19 +122,19 @@ struct DecodeParams {
     uint8_t* workspace;
     Diag* diag;
     unsigned long long* trace;
-    unsigned long long timeout_ns;   // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
-    int M, N, K, G;
-    int P;               // packed rows = N / 16 * bits
-    int tile_p;
-    int gshift;          // log2(group_size / 64): stages per group
+    uint32_t timeout_ms;             // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
+    int M, N, K;
     int n_tiles, k_iters;
-    int stages;
-    int tma_scales;      // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
-    int static_weights;
-    int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
-    int l2_prefetch;     // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
-    uint32_t partial_offset;
+    uint8_t tile_p;
+    uint8_t gshift;                  // log2(group_size / 64): stages per group
+    uint8_t stages;
+    uint8_t tma_scales;              // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
+    uint8_t static_weights;
+    uint8_t ablate;                  // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
+    uint8_t l2_prefetch;             // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
 };
+constexpr uint32_t kPartialOffset = 65536;       // workspace: [64 KB tile counters | fp32 partial sums ...]
+
 
 // Tensor-parallel extension of the parameters: a separate kernel argument that only the TP instantiation carries, so the
 // single-GPU kernel's parameter block, code and registers are exactly what they are without it (folding these fields into
@@ -144,7 +147,8 @@ struct TpParams {
     int tp, rank;
     int n_total;                  // row stride of the gathered output (= tp * N)
     uint16_t* out_peers[8];
-    unsigned* flag_peers[8];
+    long long flag_delta;         // byte distance from a rank's out_peers[r] to its arrival counter (same on every rank)
+    long long ll_delta;           // ... and to its {value, sequence} word image; 0 = no word image kept
     const unsigned* in_flag;      // arrival counter guarding A on this rank (nullptr: A is local / complete)
     unsigned in_per_step;         // arrivals on in_flag per step; expected = (epoch - 1) * in_per_step + in_offset
     unsigned in_offset;
@@ -153,7 +157,6 @@ struct TpParams {
     // element is also stored as ONE 8-byte word {value, sequence number} -- an aligned 8-byte store is single-copy atomic,
     // so a reader that sees the expected sequence number has the value: no fence, no separate flag, one NVLink
     // one-way trip.  sequence = (epoch - 1) * uses + call + 1 (grows for ever; the buffers start zeroed).
-    uint2* ll_peers[8];           // every rank's LL image of this output, [M, n_total] uint2 (nullptr: not kept)
     unsigned out_uses, out_call;
     const uint2* in_ll;           // LL image A is read from (nullptr: plain A through cp.async)
     int in_ll_stride;             // elements per row of that image
@@ -183,17 +186,17 @@ static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t 
     __trap();
 }
 
-// Lean bounded wait: one try_wait on the fast path; the bound (p.timeout_ns, 0 = none) is checked out of line
+// Lean bounded wait: one try_wait on the fast path; the bound (p.timeout_ms, 0 = none) is checked out of line
 // every 1024 failed probes (each failed try_wait already suspends the warp for a hardware-defined interval).
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const DecodeParams& p, int site, int iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && p.timeout_ns != 0) {
+        if ((++spins & 0x3ff) == 0 && p.timeout_ms != 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
+            else if (now - t0 > (uint64_t)p.timeout_ms * 1000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
         }
     }
 }
@@ -406,7 +409,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             const int tile = it / p.k_iters;
             const int k = it - tile * p.k_iters;
             const int prow = tile * 128 + r;
-            if (prow < p.P) {
+            if (prow < p.N / 16 * BITS) {
                 const uint8_t* addr = p.Q + ((size_t)prow * p.K + (size_t)k * 64) * 2;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(addr) : "memory");
             }
@@ -467,9 +470,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             for (int r = 0; r < t.tp; ++r) {
                 // the plain image is for readers outside this engine; calls whose output only feeds other qgemm_tp calls
                 // (signal_counter == 0) keep just the word image and halve their NVLink stores
-                if (t.signal_counter || t.ll_peers[r] == nullptr) t.out_peers[r][off] = v;
-                if (t.ll_peers[r] != nullptr)
-                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(t.ll_peers[r] + off), "r"((uint32_t)v), "r"(seq) : "memory");
+                if (t.signal_counter || t.ll_delta == 0) t.out_peers[r][off] = v;
+                if (t.ll_delta != 0)
+                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(reinterpret_cast<char*>(t.out_peers[r]) + t.ll_delta) + off),
+                                 "r"((uint32_t)v), "r"(seq) : "memory");
             }
         }
     };
@@ -483,7 +487,8 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         if constexpr (TP) {
             __threadfence_system();
 #pragma unroll 1
-            for (int r = 0; r < tpa.v.tp; ++r) red_release_sys_add_u32(tpa.v.flag_peers[r], 1u);
+            for (int r = 0; r < tpa.v.tp; ++r)
+                red_release_sys_add_u32(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(tpa.v.out_peers[r]) + tpa.v.flag_delta), 1u);
         }
     };
     auto tp_signals = [&]() -> bool {
@@ -516,6 +521,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     // cp.async, not TMA: as a TMA box the 512 sixteen-byte rows cost the producer ~2000 cycles of issue time per
     // block (measured), during which no weight tile could be requested.
     auto scale_step = [&](int tile, int k, int& nb, int& last_blk) {
+        const int G = p.K >> (6 + p.gshift);      // groups per row of S
         const int blk = (k >> p.gshift) >> 3;
         if (blk == last_blk) return;
         const int slot = nb % kScSlots;
@@ -527,7 +533,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             for (int r = lane; r < TN; r += 32) {
                 const int n = tile * TN + r;
                 if (n < p.N) {
-                    const uint16_t* src = p.S + (size_t)n * p.G + blk * 8;
+                    const uint16_t* src = p.S + (size_t)n * G + blk * 8;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 16), "l"(src) : "memory");
                 }
             }
@@ -539,7 +545,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 #pragma unroll
                 for (int gi = 0; gi < 8; ++gi) {
                     const int g = blk * 8 + gi;
-                    d16[r * 8 + gi] = (n < p.N && g < p.G) ? __ldg(p.S + (size_t)n * p.G + g) : (uint16_t)0;
+                    d16[r * 8 + gi] = (n < p.N && g < G) ? __ldg(p.S + (size_t)n * G + g) : (uint16_t)0;
                 }
             }
             mbar_arrive(smem_u32(&ctl->sc_full[slot]));
@@ -707,10 +713,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     uint64_t t0 = 0;
                     uint32_t spins = 0;
                     while ((int)(ld_acquire_sys_u32(tp_in_flag()) - expected) < 0) {
-                        if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
+                        if ((++spins & 0xff) == 0 && p.timeout_ms != 0) {
                             const uint64_t now = globaltimer_ns();
                             if (t0 == 0) t0 = now;
-                            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, 0u, expected, -2);
+                            else if (now - t0 > (uint64_t)p.timeout_ms * 1000000ull) wait_timeout(p.diag, DSITE_FULL, 0u, expected, -2);
                         }
                     }
                 }
@@ -737,10 +743,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         for (;;) {
                             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
                             if (f0 == expected && f1 == expected) break;
-                            if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
+                            if ((++spins & 0xff) == 0 && p.timeout_ms != 0) {
                                 const uint64_t now = globaltimer_ns();
                                 if (t0 == 0) t0 = now;
-                                else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, f0, expected, -4);
+                                else if (now - t0 > (uint64_t)p.timeout_ms * 1000000ull) wait_timeout(p.diag, DSITE_FULL, f0, expected, -4);
                             }
                         }
                         const uint32_t dst = bt + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
@@ -838,7 +844,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     if (last) {
                         const unsigned seq = out_sequence();
                         __threadfence();      // every lane: order its reads after lane 0's acquire
-                        float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
+                        float* accum = reinterpret_cast<float*>(p.workspace + kPartialOffset) + (size_t)tile * (NJ * kMb * 128);
                         const int n_base = tile * TN;
 #pragma unroll 1
                         for (int m = 0; m < p.M; ++m) {
@@ -983,7 +989,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left zero
                 // on exit), then hand over to the fix-up warp (arrival counter, last-arriver conversion) and carry on
                 // with the next segment: nothing on the streaming path waits for a global-memory round trip.
-                float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
+                float* accum = reinterpret_cast<float*>(p.workspace + kPartialOffset) + (size_t)tile * (NJ * kMb * 128);
 #pragma unroll
                 for (int j = 0; j < NFA; ++j)
 #pragma unroll
@@ -1125,17 +1131,15 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.workspace = static_cast<uint8_t*>(a.workspace);
     p.diag = a.diag;
     p.trace = a.trace;
-    p.timeout_ns = a.timeout_ns;
+    p.timeout_ms = (uint32_t)((a.timeout_ns + 999999ull) / 1000000ull);
     p.M = a.M; p.N = a.N; p.K = a.K;
-    p.G = a.K / a.group_size;
-    p.P = a.N / 16 * BITS;
     p.tile_p = a.tile_p;
     p.gshift = (a.group_size == 64) ? 0 : (a.group_size == 128) ? 1 : 2;
     p.n_tiles = (a.N + TN - 1) / TN;
     p.k_iters = a.K / 64;
     p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
     p.ablate = a.ablate;
-    p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
+    p.tma_scales = (((a.K / a.group_size) % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
     p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : 0;
     TpArg<TP> tpa{};
     if constexpr (TP) {
@@ -1143,11 +1147,16 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
         if (a.tp->tp > 8 || a.tp->rank < 0 || a.tp->rank >= a.tp->tp || a.tp->n_total != a.tp->tp * a.N || a.tp->epoch == nullptr)
             return FB_ERR_SHAPE;
         t.tp = a.tp->tp; t.rank = a.tp->rank; t.n_total = a.tp->n_total;
+        // one allocation per rank with the same layout (symmetric memory): counters and word images sit at the same
+        // distance from the plain buffer on every rank, so the kernel argument carries tp pointers + two distances
+        t.flag_delta = reinterpret_cast<char*>(a.tp->flag_peers[0]) - static_cast<char*>(a.tp->out_peers[0]);
+        t.ll_delta = a.tp->ll_peers[0] != nullptr ? static_cast<char*>(a.tp->ll_peers[0]) - static_cast<char*>(a.tp->out_peers[0]) : 0;
         for (int r = 0; r < t.tp; ++r) {
             if (a.tp->out_peers[r] == nullptr || a.tp->flag_peers[r] == nullptr) return FB_ERR_NULL;
             t.out_peers[r] = static_cast<uint16_t*>(a.tp->out_peers[r]);
-            t.flag_peers[r] = a.tp->flag_peers[r];
-            t.ll_peers[r] = static_cast<uint2*>(a.tp->ll_peers[r]);
+            if (reinterpret_cast<char*>(a.tp->flag_peers[r]) - static_cast<char*>(a.tp->out_peers[r]) != t.flag_delta) return FB_ERR_SHAPE;
+            const long long lld = a.tp->ll_peers[r] != nullptr ? static_cast<char*>(a.tp->ll_peers[r]) - static_cast<char*>(a.tp->out_peers[r]) : 0;
+            if (lld != t.ll_delta) return FB_ERR_SHAPE;
         }
         t.in_flag = a.tp->in_flag; t.in_per_step = a.tp->in_per_step; t.in_offset = a.tp->in_offset;
         t.epoch = a.tp->epoch;
@@ -1181,7 +1190,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (grid > total) grid = (int)total;
 
     constexpr size_t kCounterBytes = 65536;
-    p.partial_offset = (uint32_t)kCounterBytes;
+    static_assert(kCounterBytes == kPartialOffset, "workspace layout");
     const size_t need = kCounterBytes + (size_t)p.n_tiles * F::NJ * kMb * 128 * 4;
     if ((size_t)p.n_tiles * 4 > kCounterBytes || need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
 

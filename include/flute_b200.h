@@ -156,7 +156,8 @@ typedef struct flute_b200_tp {
      * in_ll_stride words) reads A from there and spins per word on the sequence number -- no fence, no counter: one
      * NVLink one-way trip.  sequence = (*epoch - 1) * uses + call + 1 with `uses` = producing calls per step of that
      * buffer and `call` = index of the producing call within the step (out_* for this call's output, in_* for A). */
-    void* ll_peers[8];
+    void* ll_peers[8];           /* (every rank must use ONE layout: flag_peers[r] - out_peers[r] and ll_peers[r] - out_peers[r]
+                                  * are the same for all r -- one symmetric allocation per rank) */
     unsigned out_uses, out_call;
     const void* in_ll;
     int in_ll_stride;
