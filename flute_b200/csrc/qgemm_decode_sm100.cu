@@ -110,9 +110,6 @@ struct Ctl {
     uint32_t tmem_base;
 };
 
-// Kept small on purpose: together with the 128-byte tensor map the kernel's parameter block stays under 256 bytes.  Its
-// size is a measurable per-launch cost on this part (gpurun r02ab / r02ab2, same box: 159 bytes less = 0.75-1.1 us less
-// per launch at every shape), so small integers are bytes, derived values (G, P, the scratch offset) are recomputed.
 struct DecodeParams {
     const uint16_t* A;
     const uint8_t* Q;      // packed weights [P, K] int16 (also behind the tensor map; raw pointer for the entry prefetch)
@@ -122,23 +119,25 @@ struct DecodeParams {
     uint8_t* workspace;
     Diag* diag;
     unsigned long long* trace;
-    uint32_t timeout_ms;             // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
-    int M, N, K;
+    unsigned long long timeout_ns;   // barrier-wait bound (flute_b200_set_timeout_ms); 0 = unbounded
+    int M, N, K, G;
+    int P;               // packed rows = N / 16 * bits
+    int tile_p;
+    int gshift;          // log2(group_size / 64): stages per group
     int n_tiles, k_iters;
-    uint8_t tile_p;
-    uint8_t gshift;                  // log2(group_size / 64): stages per group
-    uint8_t stages;
-    uint8_t tma_scales;              // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
-    uint8_t static_weights;
-    uint8_t ablate;                  // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
-    uint8_t l2_prefetch;             // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
+    int stages;
+    int tma_scales;      // scale rows of a block are 16-byte aligned (G % 8 == 0): cp.async, else scalar loads
+    int static_weights;
+    int ablate;          // perf ablation (tools only): 1 no MMA issue, 2 no dequant pieces, 4 no scale/accumulate
+    int l2_prefetch;     // stages the producer prefetches into L2 ahead of its shared-memory ring (0 = off)
+    uint32_t partial_offset;
 };
-constexpr uint32_t kPartialOffset = 65536;       // workspace: [64 KB tile counters | fp32 partial sums ...]
-
 
 // Tensor-parallel extension of the parameters: a separate kernel argument that only the TP instantiation carries, so the
-// single-GPU kernel's parameter block, code and registers are exactly what they are without it (folding these fields into
-// DecodeParams cost every tp = 1 launch 0.7 us: gpurun r02ab, same box, 9.12 / 8.14 / 17.97 / 12.00 -> 9.86 / 8.92 / 19.00 / 12.63 us).
+// single-GPU kernel's parameter block, code and registers are exactly what they are without it.  Measured on one box
+// (gpurun r02ab / r02ab2 / r02ab3, us per launch qkv / o / gate_up / down): fields folded into DecodeParams behind run-time
+// `if (p.tp > 1)` 9.86 / 8.92 / 19.00 / 12.63; this split 8.07 / 7.07 / 17.24 / 11.48; additionally squeezing DecodeParams
+// under 256 bytes with byte-sized fields 8.15 / 7.13 / 17.67 / 11.67 (no gain: not kept).
 struct TpParams {
     // Tensor-parallel column shard with the exchange fused in (tp > 1): the tile writer stores its [M, tile] slice into
     // EVERY rank's gathered buffer (peer-mapped pointers, NVLink) at column offset rank * N, then bumps that buffer's
@@ -186,17 +185,17 @@ static __device__ __noinline__ void wait_timeout(Diag* diag, int site, uint32_t 
     __trap();
 }
 
-// Lean bounded wait: one try_wait on the fast path; the bound (p.timeout_ms, 0 = none) is checked out of line
+// Lean bounded wait: one try_wait on the fast path; the bound (p.timeout_ns, 0 = none) is checked out of line
 // every 1024 failed probes (each failed try_wait already suspends the warp for a hardware-defined interval).
 __device__ __forceinline__ void wait(uint32_t bar, uint32_t parity, const DecodeParams& p, int site, int iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && p.timeout_ms != 0) {
+        if ((++spins & 0x3ff) == 0 && p.timeout_ns != 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > (uint64_t)p.timeout_ms * 1000000ull) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
+            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, site, bar, parity, iter);   // trap, don't hang
         }
     }
 }
@@ -409,7 +408,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             const int tile = it / p.k_iters;
             const int k = it - tile * p.k_iters;
             const int prow = tile * 128 + r;
-            if (prow < p.N / 16 * BITS) {
+            if (prow < p.P) {
                 const uint8_t* addr = p.Q + ((size_t)prow * p.K + (size_t)k * 64) * 2;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(addr) : "memory");
             }
@@ -521,7 +520,6 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     // cp.async, not TMA: as a TMA box the 512 sixteen-byte rows cost the producer ~2000 cycles of issue time per
     // block (measured), during which no weight tile could be requested.
     auto scale_step = [&](int tile, int k, int& nb, int& last_blk) {
-        const int G = p.K >> (6 + p.gshift);      // groups per row of S
         const int blk = (k >> p.gshift) >> 3;
         if (blk == last_blk) return;
         const int slot = nb % kScSlots;
@@ -533,7 +531,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             for (int r = lane; r < TN; r += 32) {
                 const int n = tile * TN + r;
                 if (n < p.N) {
-                    const uint16_t* src = p.S + (size_t)n * G + blk * 8;
+                    const uint16_t* src = p.S + (size_t)n * p.G + blk * 8;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 16), "l"(src) : "memory");
                 }
             }
@@ -545,7 +543,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 #pragma unroll
                 for (int gi = 0; gi < 8; ++gi) {
                     const int g = blk * 8 + gi;
-                    d16[r * 8 + gi] = (n < p.N && g < G) ? __ldg(p.S + (size_t)n * G + g) : (uint16_t)0;
+                    d16[r * 8 + gi] = (n < p.N && g < p.G) ? __ldg(p.S + (size_t)n * p.G + g) : (uint16_t)0;
                 }
             }
             mbar_arrive(smem_u32(&ctl->sc_full[slot]));
@@ -713,10 +711,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     uint64_t t0 = 0;
                     uint32_t spins = 0;
                     while ((int)(ld_acquire_sys_u32(tp_in_flag()) - expected) < 0) {
-                        if ((++spins & 0xff) == 0 && p.timeout_ms != 0) {
+                        if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
                             const uint64_t now = globaltimer_ns();
                             if (t0 == 0) t0 = now;
-                            else if (now - t0 > (uint64_t)p.timeout_ms * 1000000ull) wait_timeout(p.diag, DSITE_FULL, 0u, expected, -2);
+                            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, 0u, expected, -2);
                         }
                     }
                 }
@@ -743,10 +741,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         for (;;) {
                             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
                             if (f0 == expected && f1 == expected) break;
-                            if ((++spins & 0xff) == 0 && p.timeout_ms != 0) {
+                            if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
                                 const uint64_t now = globaltimer_ns();
                                 if (t0 == 0) t0 = now;
-                                else if (now - t0 > (uint64_t)p.timeout_ms * 1000000ull) wait_timeout(p.diag, DSITE_FULL, f0, expected, -4);
+                                else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, f0, expected, -4);
                             }
                         }
                         const uint32_t dst = bt + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
@@ -844,7 +842,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     if (last) {
                         const unsigned seq = out_sequence();
                         __threadfence();      // every lane: order its reads after lane 0's acquire
-                        float* accum = reinterpret_cast<float*>(p.workspace + kPartialOffset) + (size_t)tile * (NJ * kMb * 128);
+                        float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
                         const int n_base = tile * TN;
 #pragma unroll 1
                         for (int m = 0; m < p.M; ++m) {
@@ -989,7 +987,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left zero
                 // on exit), then hand over to the fix-up warp (arrival counter, last-arriver conversion) and carry on
                 // with the next segment: nothing on the streaming path waits for a global-memory round trip.
-                float* accum = reinterpret_cast<float*>(p.workspace + kPartialOffset) + (size_t)tile * (NJ * kMb * 128);
+                float* accum = reinterpret_cast<float*>(p.workspace + p.partial_offset) + (size_t)tile * (NJ * kMb * 128);
 #pragma unroll
                 for (int j = 0; j < NFA; ++j)
 #pragma unroll
@@ -1131,15 +1129,17 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     p.workspace = static_cast<uint8_t*>(a.workspace);
     p.diag = a.diag;
     p.trace = a.trace;
-    p.timeout_ms = (uint32_t)((a.timeout_ns + 999999ull) / 1000000ull);
+    p.timeout_ns = a.timeout_ns;
     p.M = a.M; p.N = a.N; p.K = a.K;
+    p.G = a.K / a.group_size;
+    p.P = a.N / 16 * BITS;
     p.tile_p = a.tile_p;
     p.gshift = (a.group_size == 64) ? 0 : (a.group_size == 128) ? 1 : 2;
     p.n_tiles = (a.N + TN - 1) / TN;
     p.k_iters = a.K / 64;
     p.static_weights = (a.flags & FB_FLAG_STATIC_WEIGHTS) ? 1 : 0;
     p.ablate = a.ablate;
-    p.tma_scales = (((a.K / a.group_size) % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
+    p.tma_scales = ((p.G % 8) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0) ? 1 : 0;   // 16-byte scale rows
     p.l2_prefetch = a.l2_prefetch >= 0 ? a.l2_prefetch : 0;
     TpArg<TP> tpa{};
     if constexpr (TP) {
@@ -1190,7 +1190,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (grid > total) grid = (int)total;
 
     constexpr size_t kCounterBytes = 65536;
-    static_assert(kCounterBytes == kPartialOffset, "workspace layout");
+    p.partial_offset = (uint32_t)kCounterBytes;
     const size_t need = kCounterBytes + (size_t)p.n_tiles * F::NJ * kMb * 128 * 4;
     if ((size_t)p.n_tiles * 4 > kCounterBytes || need + prefill_scratch_bytes(a.num_sms) > a.workspace_bytes) return FB_ERR_WORKSPACE;
 
