@@ -396,8 +396,7 @@ def run_own(args):
     tpx = None
     if tp > 1:
         progress("tensor-parallel exchange: symmetric memory rendezvous")
-        tpx = parallel.FusedGather(dev, rank, tp, [(name, M, N, LAYERS, 1 if name == "down" else 0) for name, N, K in SHAPES],
-                                   torch.bfloat16)
+        tpx = parallel.FusedGather(dev, rank, tp, [(name, M, N, LAYERS) for name, N, K in SHAPES], torch.bfloat16)
     bufs = {name: torch.empty((M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
     gathered = {name: torch.empty((tp, M, N // tp), dtype=torch.bfloat16, device=dev) for name, N, K in SHAPES}
 
@@ -407,8 +406,8 @@ def run_own(args):
         Q, S, n_loc, K = lin[name]
         launches[0] += 1
         if tp > 1 and mode == "fused":
-            # arrival counters only where something other than the next qgemm reads the buffer: the step's final output
-            return tpx.qgemm(x, Q, S, table, table2, ws, name, n_loc, K, BITS, GROUP, flags, signal_counter=last)
+            # the plain image only where something other than the next qgemm reads the buffer: the step's final output
+            return tpx.qgemm(x, Q, S, table, table2, ws, name, n_loc, K, BITS, GROUP, flags, plain=last)
         out = bufs[name]
         rc = _lib.lib.flute_b200_qgemm(x.data_ptr(), Q.data_ptr(), out.data_ptr(), S.data_ptr(), table.data_ptr(),
                                        table2.data_ptr(), ws.data_ptr(), ws.numel(), M, n_loc, K, BITS, GROUP, 32,
@@ -492,7 +491,7 @@ def run_own(args):
         ms_nccl = timed(lambda: token(x0, linear_cabi, "nccl"), max(5, args.steps // 5), 2)
         tp_record = {"exchange": "fused into the GEMM epilogue: NVLink peer stores of {value, sequence} words into every rank's "
                                  "symmetric-memory buffer; the consuming launch's activation warp spins on the sequence "
-                                 "numbers (no fence, no collective kernel); arrival counters only for the step's final output",
+                                 "numbers (no fence, no collective kernel); a system-scope publish + wait only after the step's final output",
                      "tok_s_fused_exchange": tok_s, "tok_s_without_exchange": 1e3 / ms_none,
                      "tok_s_nccl_allgather_eager": 1e3 / ms_nccl,
                      "bytes_exchanged_per_rank_per_step": LAYERS * sum(M * N // tp * 2 * (tp - 1) for _, N, K in SHAPES)}

@@ -34,7 +34,7 @@ EXPORTS = (
     "flute_b200_set_variant",
     "flute_b200_dispatch_name",
     "flute_b200_qgemm_tp",
-    "flute_b200_tp_tiles",
+    "flute_b200_tp_publish",
     "flute_b200_tp_advance",
     "flute_b200_tp_wait",
 )
@@ -49,10 +49,9 @@ _u = ctypes.c_uint
 
 class TpDesc(ctypes.Structure):
     """`flute_b200_tp` of include/flute_b200.h (tensor-parallel fused exchange descriptor)."""
-    _fields_ = [("tp", _i), ("rank", _i), ("n_total", _i), ("out_peers", _vp * 8), ("flag_peers", _vp * 8),
-                ("in_flag", _vp), ("in_per_step", _u), ("in_offset", _u), ("epoch", _vp),
-                ("ll_peers", _vp * 8), ("out_uses", _u), ("out_call", _u), ("in_ll", _vp), ("in_ll_stride", _i),
-                ("in_uses", _u), ("in_call", _u), ("signal_counter", _i)]
+    _fields_ = [("tp", _i), ("rank", _i), ("n_total", _i), ("out_peers", _vp * 8), ("ll_peers", _vp * 8), ("write_plain", _i),
+                ("out_uses", _u), ("out_call", _u), ("in_ll", _vp), ("in_ll_stride", _i), ("in_uses", _u), ("in_call", _u),
+                ("epoch", _vp)]
 
 
 
@@ -95,8 +94,8 @@ def _load() -> ctypes.CDLL:
     lib.flute_b200_qgemm_tp.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp,
                                         ctypes.POINTER(TpDesc)]
     lib.flute_b200_qgemm_tp.restype = _i
-    lib.flute_b200_tp_tiles.argtypes = [_i, _i]
-    lib.flute_b200_tp_tiles.restype = _i
+    lib.flute_b200_tp_publish.argtypes = [ctypes.POINTER(_vp), _i, _i, _vp]
+    lib.flute_b200_tp_publish.restype = _i
     lib.flute_b200_tp_advance.argtypes = [_vp, _i, _vp]
     lib.flute_b200_tp_advance.restype = _i
     lib.flute_b200_tp_wait.argtypes = [_vp, _u, _u, _vp, _i, _vp]

@@ -142,7 +142,7 @@ int run_qgemm(const void* A, const void* Q, void* D, const void* S, const void* 
     a.ablate = g_ablate;
     a.l2_prefetch = g_l2_prefetch;
     a.tp = tp;
-    if (tp != nullptr && tp->tp > 1 && !(M <= 4 && (num_bits == 4 || num_bits == 2)))
+    if (tp != nullptr && !(M <= 4 && (num_bits == 4 || num_bits == 2)))
         return fail(FB_ERR_SHAPE, "tensor-parallel fused exchange: decode shapes only (M <= 4 at 2/4 bits), got M=%d bits=%d", M, num_bits);
     a.timeout_ns = (g_timeout_ms > 0) ? (uint64_t)g_timeout_ms * 1000000ull : 0ull;
     a.force_mb = force_mb; a.force_stages = force_stages; a.force_grid = force_grid; a.force_streamk = force_streamk;
@@ -186,12 +186,6 @@ int flute_b200_qgemm_tp(const void* A, const void* Q, const void* S, const void*
                      device, stream, 0, 0, 0, -1, nullptr, tp);
 }
 
-int flute_b200_tp_tiles(int N, int num_bits) {
-    const int cols = fb::decode_tile_columns(num_bits);
-    if (cols <= 0 || N <= 0) return FB_ERR_SHAPE;
-    return (N + cols - 1) / cols;
-}
-
 int flute_b200_tp_advance(unsigned* epoch, int device, void* stream) {
     if (epoch == nullptr) return fail(FB_ERR_NULL, "null epoch pointer");
     int rc = probe_device(device);
@@ -200,6 +194,18 @@ int flute_b200_tp_advance(unsigned* epoch, int device, void* stream) {
     if (guard.rc != FB_OK) return fail(guard.rc, "cudaSetDevice(%d) failed", device);
     rc = fb::tp_advance_launch(epoch, static_cast<cudaStream_t>(stream));
     return rc == FB_OK ? FB_OK : fail(rc, "tp_advance launch failed");
+}
+
+int flute_b200_tp_publish(unsigned* const* flag_peers, int tp, int device, void* stream) {
+    if (flag_peers == nullptr || tp < 1 || tp > 8) return fail(FB_ERR_SHAPE, "tp_publish: tp=%d", tp);
+    for (int r = 0; r < tp; ++r)
+        if (flag_peers[r] == nullptr) return fail(FB_ERR_NULL, "null counter pointer");
+    int rc = probe_device(device);
+    if (rc != FB_OK) return rc;
+    DeviceGuard guard(device);
+    if (guard.rc != FB_OK) return fail(guard.rc, "cudaSetDevice(%d) failed", device);
+    rc = fb::tp_publish_launch(flag_peers, tp, static_cast<cudaStream_t>(stream));
+    return rc == FB_OK ? FB_OK : fail(rc, "tp_publish launch failed");
 }
 
 int flute_b200_tp_wait(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, int device, void* stream) {

@@ -139,28 +139,25 @@ struct DecodeParams {
 // `if (p.tp > 1)` 9.86 / 8.92 / 19.00 / 12.63; this split 8.07 / 7.07 / 17.24 / 11.48; additionally squeezing DecodeParams
 // under 256 bytes with byte-sized fields 8.15 / 7.13 / 17.67 / 11.67 (no gain: not kept).
 struct TpParams {
-    // Tensor-parallel column shard with the exchange fused in (tp > 1): the tile writer stores its [M, tile] slice into
-    // EVERY rank's gathered buffer (peer-mapped pointers, NVLink) at column offset rank * N, then bumps that buffer's
-    // arrival counter on every rank (release, system scope); the activation warp of the consuming launch waits on its
-    // own rank's counter of the buffer A lives in (acquire) -- no collective kernel, no host involvement.
+    // Tensor-parallel column shard with the exchange fused in: the tile writer stores its [M, tile] slice into EVERY rank's
+    // gathered buffer (peer-mapped pointers, NVLink) at column offset rank * N -- as a plain T image (for readers outside
+    // this engine, optional) and as ONE 8-byte word {value, sequence number} per element (the NCCL "LL" idea): an aligned
+    // 8-byte store is single-copy atomic, so a reader that sees the expected sequence number has the value -- no fence, no
+    // separate flag, one NVLink one-way trip.  The activation warp of the consuming launch reads A from that word image
+    // and spins per word.  sequence = (epoch - 1) * uses + call + 1 (grows for ever; the buffers start zeroed).
+    // All accesses here are relaxed at GPU scope: peer stores travel over NVLink into the destination's L2, where the
+    // destination's L1-bypassing loads find them.  System-scope fences / reductions (arrival counters for readers that
+    // are not qgemm launches) live in the two tiny kernels below, not in this one.
     int tp, rank;
     int n_total;                  // row stride of the gathered output (= tp * N)
-    uint16_t* out_peers[8];
-    long long flag_delta;         // byte distance from a rank's out_peers[r] to its arrival counter (same on every rank)
-    long long ll_delta;           // ... and to its {value, sequence} word image; 0 = no word image kept
-    const unsigned* in_flag;      // arrival counter guarding A on this rank (nullptr: A is local / complete)
-    unsigned in_per_step;         // arrivals on in_flag per step; expected = (epoch - 1) * in_per_step + in_offset
-    unsigned in_offset;
-    const unsigned* epoch;        // device word: step number (>= 1)
-    // Low-latency hand-over between two qgemm launches (the NCCL "LL" idea): next to the plain buffer every output
-    // element is also stored as ONE 8-byte word {value, sequence number} -- an aligned 8-byte store is single-copy atomic,
-    // so a reader that sees the expected sequence number has the value: no fence, no separate flag, one NVLink
-    // one-way trip.  sequence = (epoch - 1) * uses + call + 1 (grows for ever; the buffers start zeroed).
+    uint16_t* out_peers[8];       // every rank's plain image [M, n_total]
+    long long ll_delta;           // byte distance from a rank's plain image to its word image (same on every rank)
+    int write_plain;              // also keep the plain image current (0: every reader is a qgemm_tp launch)
     unsigned out_uses, out_call;
-    const uint2* in_ll;           // LL image A is read from (nullptr: plain A through cp.async)
+    const uint2* in_ll;           // word image A is read from (nullptr: plain A through cp.async)
     int in_ll_stride;             // elements per row of that image
     unsigned in_uses, in_call;
-    int signal_counter;           // also bump the arrival counters (needed only when something other than a qgemm_tp reads D)
+    const unsigned* epoch;        // device word: step number (>= 1)
 };
 template <bool TP>
 struct TpArg {
@@ -263,6 +260,11 @@ __device__ __forceinline__ int atom_add_acq_rel(int* addr, int v) {
     int old;
     asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
     return old;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* addr) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void red_release_sys_add_u32(unsigned* addr, unsigned v) {
     asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
@@ -468,38 +470,15 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 #pragma unroll 1
             for (int r = 0; r < t.tp; ++r) {
                 // the plain image is for readers outside this engine; calls whose output only feeds other qgemm_tp calls
-                // (signal_counter == 0) keep just the word image and halve their NVLink stores
-                if (t.signal_counter || t.ll_delta == 0) t.out_peers[r][off] = v;
-                if (t.ll_delta != 0)
-                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(reinterpret_cast<char*>(t.out_peers[r]) + t.ll_delta) + off),
-                                 "r"((uint32_t)v), "r"(seq) : "memory");
+                // (write_plain == 0) keep just the word image and halve their NVLink stores
+                if (t.write_plain) t.out_peers[r][off] = v;
+                asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2*>(reinterpret_cast<char*>(t.out_peers[r]) + t.ll_delta) + off),
+                             "r"((uint32_t)v), "r"(seq) : "memory");
             }
         }
     };
     auto out_sequence = [&]() -> unsigned {
-        if constexpr (TP) return (ld_acquire_sys_u32(tpa.v.epoch) - 1u) * tpa.v.out_uses + tpa.v.out_call + 1u;
-        else return 0u;
-    };
-    // after a tile's stores (made visible system-wide by ONE fence of the signalling thread, which the CTA-level barrier
-    // before it makes cumulative over the other threads' stores): one arrival on every rank's counter
-    auto signal_tile = [&]() {
-        if constexpr (TP) {
-            __threadfence_system();
-#pragma unroll 1
-            for (int r = 0; r < tpa.v.tp; ++r)
-                red_release_sys_add_u32(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(tpa.v.out_peers[r]) + tpa.v.flag_delta), 1u);
-        }
-    };
-    auto tp_signals = [&]() -> bool {
-        if constexpr (TP) return tpa.v.signal_counter != 0;
-        else return false;
-    };
-    auto tp_in_flag = [&]() -> const unsigned* {
-        if constexpr (TP) return tpa.v.in_flag;
-        else return nullptr;
-    };
-    auto tp_expected_arrivals = [&]() -> unsigned {
-        if constexpr (TP) return (ld_acquire_sys_u32(tpa.v.epoch) - 1u) * tpa.v.in_per_step + tpa.v.in_offset;
+        if constexpr (TP) return (ld_relaxed_gpu_u32(tpa.v.epoch) - 1u) * tpa.v.out_uses + tpa.v.out_call + 1u;
         else return 0u;
     };
     auto tp_in_ll = [&]() -> const uint2* {
@@ -511,7 +490,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         else return 0;
     };
     auto tp_expected_sequence = [&]() -> unsigned {
-        if constexpr (TP) return (ld_acquire_sys_u32(tpa.v.epoch) - 1u) * tpa.v.in_uses + tpa.v.in_call + 1u;
+        if constexpr (TP) return (ld_relaxed_gpu_u32(tpa.v.epoch) - 1u) * tpa.v.in_uses + tpa.v.in_call + 1u;
         else return 0u;
     };
 
@@ -704,22 +683,6 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             // the wait for the previous kernel.
             if (!kScaleWarpExists && p.static_weights) scale_step(tile, k, nb, last_blk);
             if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
-            if (TP && tp_in_flag() != nullptr) {
-                // tensor parallel: A is a gathered buffer; every rank's slice must have arrived (acquire, system scope)
-                if (lane == 0) {
-                    const unsigned expected = tp_expected_arrivals();
-                    uint64_t t0 = 0;
-                    uint32_t spins = 0;
-                    while ((int)(ld_acquire_sys_u32(tp_in_flag()) - expected) < 0) {
-                        if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
-                            const uint64_t now = globaltimer_ns();
-                            if (t0 == 0) t0 = now;
-                            else if (now - t0 > p.timeout_ns) wait_timeout(p.diag, DSITE_FULL, 0u, expected, -2);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
             if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
@@ -739,7 +702,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         uint64_t t0 = 0;
                         uint32_t spins = 0;
                         for (;;) {
-                            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
+                            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
                             if (f0 == expected && f1 == expected) break;
                             if ((++spins & 0xff) == 0 && p.timeout_ns != 0) {
                                 const uint64_t now = globaltimer_ns();
@@ -860,10 +823,6 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                                     if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]), seq);
                                 }
                         }
-                        if (tp_signals()) {
-                            __syncwarp();
-                            if (lane == 0) signal_tile();
-                        }
                     }
                     if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
                 }
@@ -978,10 +937,6 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         for (int m = 0; m < MC; ++m)
                             if (m < p.M) store_out(m, n, f32_to_t<BF16>(acc[j][m]), seq);
                     }
-                }
-                if (tp_signals()) {   // whole tile written by the apply warps: one arrival per rank once all are done
-                    asm volatile("bar.sync 2, %0;" ::"n"(kApplyWarps * 32) : "memory");
-                    if (warp == kApplyWarp0 && lane == 0) signal_tile();
                 }
             } else {
                 // Partial K range: fire-and-forget fp32 reductions into the tile's scratch (zero on entry, left zero
@@ -1144,26 +1099,23 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     TpArg<TP> tpa{};
     if constexpr (TP) {
         TpParams& t = tpa.v;
-        if (a.tp->tp > 8 || a.tp->rank < 0 || a.tp->rank >= a.tp->tp || a.tp->n_total != a.tp->tp * a.N || a.tp->epoch == nullptr)
+        if (a.tp->tp < 1 || a.tp->tp > 8 || a.tp->rank < 0 || a.tp->rank >= a.tp->tp || a.tp->n_total != a.tp->tp * a.N || a.tp->epoch == nullptr)
             return FB_ERR_SHAPE;
         t.tp = a.tp->tp; t.rank = a.tp->rank; t.n_total = a.tp->n_total;
-        // one allocation per rank with the same layout (symmetric memory): counters and word images sit at the same
-        // distance from the plain buffer on every rank, so the kernel argument carries tp pointers + two distances
-        t.flag_delta = reinterpret_cast<char*>(a.tp->flag_peers[0]) - static_cast<char*>(a.tp->out_peers[0]);
-        t.ll_delta = a.tp->ll_peers[0] != nullptr ? static_cast<char*>(a.tp->ll_peers[0]) - static_cast<char*>(a.tp->out_peers[0]) : 0;
+        // one allocation per rank with the same layout (symmetric memory): the word image sits at the same distance from
+        // the plain image on every rank, so the kernel argument carries tp pointers + one distance
+        if (a.tp->out_peers[0] == nullptr || a.tp->ll_peers[0] == nullptr) return FB_ERR_NULL;
+        t.ll_delta = static_cast<char*>(a.tp->ll_peers[0]) - static_cast<char*>(a.tp->out_peers[0]);
         for (int r = 0; r < t.tp; ++r) {
-            if (a.tp->out_peers[r] == nullptr || a.tp->flag_peers[r] == nullptr) return FB_ERR_NULL;
+            if (a.tp->out_peers[r] == nullptr || a.tp->ll_peers[r] == nullptr) return FB_ERR_NULL;
             t.out_peers[r] = static_cast<uint16_t*>(a.tp->out_peers[r]);
-            if (reinterpret_cast<char*>(a.tp->flag_peers[r]) - static_cast<char*>(a.tp->out_peers[r]) != t.flag_delta) return FB_ERR_SHAPE;
-            const long long lld = a.tp->ll_peers[r] != nullptr ? static_cast<char*>(a.tp->ll_peers[r]) - static_cast<char*>(a.tp->out_peers[r]) : 0;
-            if (lld != t.ll_delta) return FB_ERR_SHAPE;
+            if (static_cast<char*>(a.tp->ll_peers[r]) - static_cast<char*>(a.tp->out_peers[r]) != t.ll_delta) return FB_ERR_SHAPE;
         }
-        t.in_flag = a.tp->in_flag; t.in_per_step = a.tp->in_per_step; t.in_offset = a.tp->in_offset;
         t.epoch = a.tp->epoch;
+        t.write_plain = a.tp->write_plain;
         t.out_uses = a.tp->out_uses; t.out_call = a.tp->out_call;
         t.in_ll = static_cast<const uint2*>(a.tp->in_ll); t.in_ll_stride = a.tp->in_ll_stride;
         t.in_uses = a.tp->in_uses; t.in_call = a.tp->in_call;
-        t.signal_counter = a.tp->signal_counter;
         if (t.in_ll != nullptr && ((reinterpret_cast<uintptr_t>(t.in_ll) & 15) != 0 || (t.in_ll_stride & 1) != 0)) return FB_ERR_SHAPE;
     }
 
@@ -1232,7 +1184,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
 
 template <int BITS, bool BF16>
 static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
-    if (a.tp != nullptr && a.tp->tp > 1) {        // tensor-parallel fused exchange: its own instantiations (M <= 4)
+    if (a.tp != nullptr) {        // tensor-parallel fused exchange (tp >= 1): its own instantiations (M <= 4)
         if (a.M == 1) return launch_t<BITS, BF16, 1, true>(a, stream);
         if (a.M <= 4) return launch_t<BITS, BF16, 4, true>(a, stream);
         return FB_ERR_SHAPE;
@@ -1245,10 +1197,19 @@ static int launch_mc(const QgemmArgs& a, cudaStream_t stream) {
 
 }  // namespace dec
 
-int decode_tile_columns(int bits) { return bits == 4 ? dec::DCfg<4>::NJ * 128 : bits == 2 ? dec::DCfg<2>::NJ * 128 : 0; }
 
 namespace dec {
 __global__ void tp_advance_kernel(unsigned* epoch) { *epoch += 1u; }
+// System-scope side of the exchange, for readers that are NOT qgemm_tp launches: `publish` runs after the launches whose
+// output it announces (stream order: their stores are complete), makes them visible system-wide and bumps the arrival
+// counter of that output on every rank; `wait` spins until this rank's counter has seen every rank's publish of the step.
+struct TpFlags {
+    unsigned* flag[8];
+};
+__global__ void tp_publish_kernel(TpFlags f, int tp) {
+    __threadfence_system();
+    for (int r = 0; r < tp; ++r) red_release_sys_add_u32(f.flag[r], 1u);
+}
 __global__ void tp_wait_kernel(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, uint64_t timeout_ns,
                                Diag* diag) {
     const unsigned expected = (ld_acquire_sys_u32(epoch) - 1u) * per_step + offset;
@@ -1266,6 +1227,12 @@ __global__ void tp_wait_kernel(const unsigned* flag, unsigned per_step, unsigned
 
 int tp_advance_launch(unsigned* epoch, cudaStream_t stream) {
     dec::tp_advance_kernel<<<1, 1, 0, stream>>>(epoch);
+    return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_LAUNCH;
+}
+int tp_publish_launch(unsigned* const* flags, int tp, cudaStream_t stream) {
+    dec::TpFlags f{};
+    for (int r = 0; r < tp && r < 8; ++r) f.flag[r] = flags[r];
+    dec::tp_publish_kernel<<<1, 1, 0, stream>>>(f, tp);
     return cudaGetLastError() == cudaSuccess ? FB_OK : FB_ERR_LAUNCH;
 }
 int tp_wait_launch(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, uint64_t timeout_ns, Diag* diag,

@@ -87,8 +87,8 @@ inline size_t prefill_scratch_bytes(int num_sms) { return (size_t)num_sms * 2 * 
 bool qgemm_prefill_supported(const QgemmArgs& a);
 int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream);
 int qgemm_max_mb(int bits);
-int decode_tile_columns(int bits);   // output columns per decode-kernel tile (arrival unit of the fused exchange)
 int tp_advance_launch(unsigned* epoch, cudaStream_t stream);
+int tp_publish_launch(unsigned* const* flags, int tp, cudaStream_t stream);
 int tp_wait_launch(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, uint64_t timeout_ns, Diag* diag,
                    cudaStream_t stream);
 const char* qgemm_dispatch_name(int M, int num_bits, bool bf16);

@@ -56,55 +56,55 @@ class FusedGather:
     """The forward exchange of a column-sharded linear, fused into the GEMM.
 
     One symmetric-memory allocation per rank (torch.distributed._symmetric_memory: CUDA VMM buffers mapped into every
-    peer over NVLink) holds, for every named output, the gathered activation buffer [M, N_total] and its arrival
-    counter.  `qgemm` calls `flute_b200_qgemm_tp`: the kernel's epilogue stores this rank's [M, N_total / tp] slice
-    into every rank's buffer and bumps every rank's counter; when the activations passed in live in one of these
-    buffers, the kernel first waits for that buffer's counter.  There is no collective kernel and nothing to
-    synchronise on the host, so a whole token step captures into one CUDA graph.
+    peer over NVLink) holds, for every named output, the gathered activation buffer [M, N_total] in T (the "plain image"),
+    its "word image" ([M, N_total] 8-byte words {value, sequence number}) and an arrival counter.  `qgemm` calls
+    `flute_b200_qgemm_tp`: the kernel's epilogue stores this rank's [M, N_total / tp] slice into every rank's word image;
+    when the activations passed in live in one of these buffers, the kernel reads them from the word image and spins per
+    word on the sequence number.  No collective kernel, no fence between producer and consumer, nothing to synchronise on
+    the host: a whole token step captures into one CUDA graph.
 
         fg = FusedGather(dev, rank, tp, [("qkv", 1, 6144, 32), ...], torch.bfloat16)   # name, M, N_total, uses per step
-                                                                      # [, uses per step that also bump the counters]
-        fg.begin_step();  y = fg.qgemm(x, Q_r, S_r, table, table2, ws, "qkv", n_loc, K, 4, 64, flags);  ...;  fg.end_step("down")
+        fg.begin_step();  y = fg.qgemm(x, Q_r, S_r, table, table2, ws, "qkv", n_loc, K, 4, 64, flags);  ...
+        out = fg.qgemm(..., "down", ..., plain=True);  fg.end_step("down")           # `out` is data after end_step
 
     Every rank must issue the same sequence of calls per step; each named buffer is written `uses` times per step.
+    The tensor `qgemm` returns is a handle for the next `qgemm`; it holds current data only for calls made with
+    `plain=True` and only after `end_step(name)` (publish + wait: the system-scope side of the exchange).
     """
 
     def __init__(self, device: torch.device, rank: int, tp: int, outputs: Sequence[Tuple[str, int, int, int]],
-                 dtype: torch.dtype, group: Optional[dist.ProcessGroup] = None, num_bits: int = 4) -> None:
+                 dtype: torch.dtype, group: Optional[dist.ProcessGroup] = None) -> None:
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
-        self.device, self.rank, self.tp, self.dtype, self.num_bits = device, rank, tp, dtype, num_bits
+        self.device, self.rank, self.tp, self.dtype = device, rank, tp, dtype
         group = group if group is not None else dist.group.WORLD
-        flag_bytes = 128 * len(outputs)
-        offs, ll_offs, off = {}, {}, flag_bytes
-        outputs = [tuple(o) + ((o[3],) if len(o) == 4 else ()) for o in outputs]     # signalled uses default to all uses
-        for name, M, n_total, uses, signalled in outputs:
+        offs, ll_offs, off = {}, {}, 128 * len(outputs)      # [counters, 128 B apart | per output: plain image, word image]
+        for name, M, n_total, uses in outputs:
             offs[name] = off
             off += (M * n_total * 2 + 255) // 256 * 256
-            ll_offs[name] = off                      # {value, sequence} image: 8 bytes per element
+            ll_offs[name] = off
             off += (M * n_total * 8 + 255) // 256 * 256
         self.buf = symm_mem.empty(off, dtype=torch.uint8, device=device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, group)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         torch.cuda.synchronize(device)
-        dist.barrier(group)                      # every rank's counters are zero before anyone's first store can land
+        dist.barrier(group)                      # every rank's images are zero before anyone's first store can land
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.out: Dict[str, dict] = {}
-        for i, (name, M, n_total, uses, signalled) in enumerate(outputs):
-            n_loc = n_total // tp
-            arrivals = tp * _lib.lib.flute_b200_tp_tiles(n_loc, num_bits)
+        for i, (name, M, n_total, uses) in enumerate(outputs):
             view = self.buf[offs[name]:offs[name] + M * n_total * 2].view(dtype).view(M, n_total)
-            self.out[name] = dict(M=M, n_total=n_total, uses=uses, signalled_uses=signalled, signalled=0, arrivals=arrivals, view=view,
-                                  base=ptrs[rank] + offs[name], nbytes=M * n_total * 2,
-                                  out_peers=[p + offs[name] for p in ptrs], flag_peers=[p + 128 * i for p in ptrs],
-                                  ll_base=ptrs[rank] + ll_offs[name], ll_peers=[p + ll_offs[name] for p in ptrs], calls=0)
+            flags = (ctypes.c_void_p * 8)(*[p + 128 * i for p in ptrs] + [None] * (8 - tp))
+            self.out[name] = dict(M=M, n_total=n_total, uses=uses, view=view, base=ptrs[rank] + offs[name], nbytes=M * n_total * 2,
+                                  out_peers=[p + offs[name] for p in ptrs], ll_base=ptrs[rank] + ll_offs[name],
+                                  ll_peers=[p + ll_offs[name] for p in ptrs], flags=flags, my_flag=ptrs[rank] + 128 * i,
+                                  calls=0, published=0)
 
     def begin_step(self) -> None:
         for o in self.out.values():
             o["calls"] = 0
-            o["signalled"] = 0
+            o["published"] = 0
         st = torch.cuda.current_stream(self.device).cuda_stream
         self._lib.check(self._lib.lib.flute_b200_tp_advance(self.epoch.data_ptr(), self.device.index, st))
 
@@ -118,38 +118,34 @@ class FusedGather:
 
     def qgemm(self, x: torch.Tensor, Q: torch.Tensor, S: torch.Tensor, table: torch.Tensor, table2: torch.Tensor,
               workspace: torch.Tensor, name: str, n_loc: int, K: int, num_bits: int, group_size: int, flags: int,
-              tile_P: int = 32, signal_counter: Optional[bool] = None) -> torch.Tensor:
-        """`signal_counter=False`: every reader of this output is another `qgemm` of this object (they take the
-        low-latency word image), so neither the arrival counters nor the plain image are written -- the returned view
-        is then only a handle for the next `qgemm`, not data; `end_step` needs a signalled call of its buffer."""
+              tile_P: int = 32, plain: bool = False) -> torch.Tensor:
+        """This rank's column slice of linear `name`, written into every rank's gathered buffer.  `plain=True` also keeps
+        the plain image current (for `end_step` and readers outside this class)."""
         _lib = self._lib
         o = self.out[name]
         M = x.shape[0]
         if M != o["M"] or n_loc * self.tp != o["n_total"] or x.stride(-1) != 1:
             raise ValueError("flute_b200: FusedGather.qgemm shape mismatch")
+        if o["calls"] >= o["uses"]:
+            raise ValueError(f"flute_b200: `{name}` written more than its declared {o['uses']} times per step")
         d = _lib.TpDesc()
         d.tp, d.rank, d.n_total = self.tp, self.rank, o["n_total"]
         for r in range(self.tp):
             d.out_peers[r] = o["out_peers"][r]
-            d.flag_peers[r] = o["flag_peers"][r]
-        for r in range(self.tp):
             d.ll_peers[r] = o["ll_peers"][r]
+        d.write_plain = 1 if plain else 0
         d.out_uses, d.out_call = o["uses"], o["calls"]
-        if signal_counter is None:
-            signal_counter = o["signalled_uses"] == o["uses"]
-        d.signal_counter = 1 if signal_counter else 0
         src, elem_off = self._source_of(x)
         if src is None and not x.is_contiguous():
             raise ValueError("flute_b200: local activations must be contiguous")
         if src is not None:
             if src["calls"] < 1:
                 raise ValueError("flute_b200: FusedGather.qgemm reads a gathered buffer that was not written in this step")
-            if x.stride(0) != src["n_total"] and M > 1:
+            if M > 1 and x.stride(0) != src["n_total"]:
                 raise ValueError("flute_b200: activations must be rows of the gathered buffer")
-            d.in_ll = src["ll_base"] + 8 * elem_off          # the low-latency image of the same elements
+            d.in_ll = src["ll_base"] + 8 * elem_off          # the word image of the same elements
             d.in_ll_stride = src["n_total"]
             d.in_uses, d.in_call = src["uses"], src["calls"] - 1
-            d.in_flag = None                                  # (the sequence numbers are the guard)
         d.epoch = self.epoch.data_ptr()
         code = _lib.BF16 if self.dtype == torch.bfloat16 else _lib.F16
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -158,15 +154,16 @@ class FusedGather:
                                           code, flags, self.device.index, st, ctypes.byref(d))
         _lib.check(rc)
         o["calls"] += 1
-        o["signalled"] += 1 if signal_counter else 0
         return o["view"]
 
     def end_step(self, name: str) -> None:
-        """Stream-ordered wait for the last write of `name` in this step (before a non-flute consumer reads it)."""
+        """Make the latest `plain=True` write of `name` readable by anything on this stream: publish this rank's stores
+        (system-scope fence + one arrival on every rank's counter), then wait for all `tp` arrivals of the step."""
         o = self.out[name]
+        if o["published"]:
+            raise ValueError(f"flute_b200: `{name}` already published in this step")
         st = torch.cuda.current_stream(self.device).cuda_stream
-        if o["signalled"] < 1:
-            raise ValueError(f"flute_b200: no call of this step bumped the counters of `{name}`")
-        rc = self._lib.lib.flute_b200_tp_wait(o["flag_peers"][self.rank], o["signalled_uses"] * o["arrivals"], o["signalled"] * o["arrivals"],
-                                              self.epoch.data_ptr(), self.device.index, st)
-        self._lib.check(rc)
+        lib = self._lib.lib
+        self._lib.check(lib.flute_b200_tp_publish(o["flags"], self.tp, self.device.index, st))
+        self._lib.check(lib.flute_b200_tp_wait(o["my_flag"], self.tp, self.tp, self.epoch.data_ptr(), self.device.index, st))
+        o["published"] = 1

@@ -130,51 +130,45 @@ FLUTE_B200_API int flute_b200_max_batch_tile(int num_bits);
  *
  * Rank r of tp owns output columns [r*N, (r+1)*N) of an n_total = tp*N wide linear (its Q / S row slices,
  * flute_b200/parallel.py).  flute_b200_qgemm_tp computes them like flute_b200_qgemm, but the kernel's epilogue stores
- * the slice straight into EVERY rank's gathered output buffer [M, n_total] (out_peers: peer-mapped device pointers,
- * e.g. torch symmetric memory over NVLink) and then bumps that buffer's arrival counter on every rank
- * (flag_peers; red.release.sys).  If `in_flag` is non-NULL the activations A live in such a gathered buffer: the
- * kernel waits (ld.acquire.sys) until in_flag has received all of this step's arrivals before it reads A.  Counters
- * only ever grow: the expected value is (*epoch - 1) * in_per_step + in_offset, where *epoch is the step number
- * (>= 1, advanced once per step by flute_b200_tp_advance on the same stream), in_per_step the arrivals the buffer
- * receives per step and in_offset the arrivals it must have received within the step before this call may read it
- * (a buffer written by L producing calls per step: in_per_step = L * a, in_offset = (l + 1) * a for the consumer of
- * the l-th, with a = tp * flute_b200_tp_tiles(N_producer, num_bits)).  No collective kernel and no host
- * synchronisation are involved; the call is CUDA-graph capturable.  Decode shapes only (M <= 4 at 2 / 4 bits).
+ * the slice straight into EVERY rank's gathered output -- peer-mapped device pointers (e.g. torch symmetric memory over
+ * NVLink): out_peers[r] is rank r's plain image [M, n_total] in T (kept current only if write_plain), ll_peers[r] its
+ * "word image": [M, n_total] 8-byte words {value, sequence number}, zero-initialised once.  A consumer call given
+ * `in_ll` (the word image of the buffer its A lives in, at A's first element; row stride in_ll_stride words) reads A
+ * from there and spins per word until it carries the expected sequence number: an aligned 8-byte store is single-copy
+ * atomic, so no fence, no flag and no collective kernel sit between producer and consumer -- one NVLink one-way trip.
+ * sequence = (*epoch - 1) * uses + call + 1, with `uses` = producing calls per step of that buffer, `call` = index of the
+ * producing call within the step (out_* for this call's output, in_* for A) and *epoch the step number (a device word,
+ * >= 1, advanced once per step by flute_b200_tp_advance on the same stream).  CUDA-graph capturable; every rank issues
+ * the same sequence of calls.  Decode shapes only (M <= 4 at 2 / 4 bits).  Every rank uses ONE layout: ll_peers[r] -
+ * out_peers[r] is the same for all r (one symmetric allocation per rank).
+ *
+ * Readers that are not qgemm_tp calls (the copy of the step's result, another library's kernel) take the plain image:
+ * the producing call sets write_plain, then flute_b200_tp_publish (after it, same stream) makes this rank's stores
+ * visible system-wide and bumps that output's arrival counter on every rank, and flute_b200_tp_wait holds the stream
+ * until this rank's counter has seen all tp publishes of the step.
  */
 typedef struct flute_b200_tp {
     int tp, rank;
     int n_total;                 /* columns of the gathered output = tp * N */
-    void* out_peers[8];          /* every rank's [M, n_total] buffer for THIS output */
-    unsigned* flag_peers[8];     /* every rank's arrival counter for THIS output */
-    const unsigned* in_flag;     /* this rank's arrival counter guarding A, or NULL */
-    unsigned in_per_step;
-    unsigned in_offset;
-    const unsigned* epoch;       /* device word holding the step number */
-    /* Low-latency hand-over between two qgemm_tp calls: besides the plain buffer every output element is also stored as
-     * one 8-byte word {value, sequence number} into ll_peers[r] ([M, n_total] such words on every rank; NULL = not kept).
-     * A consumer call given `in_ll` (the word image of the buffer its A lives in, at A's first element; row stride
-     * in_ll_stride words) reads A from there and spins per word on the sequence number -- no fence, no counter: one
-     * NVLink one-way trip.  sequence = (*epoch - 1) * uses + call + 1 with `uses` = producing calls per step of that
-     * buffer and `call` = index of the producing call within the step (out_* for this call's output, in_* for A). */
-    void* ll_peers[8];           /* (every rank must use ONE layout: flag_peers[r] - out_peers[r] and ll_peers[r] - out_peers[r]
-                                  * are the same for all r -- one symmetric allocation per rank) */
+    void* out_peers[8];          /* every rank's plain image [M, n_total] of THIS output */
+    void* ll_peers[8];           /* every rank's word image [M, n_total] x 8 bytes of THIS output */
+    int write_plain;             /* 0: every reader of this output is a qgemm_tp call using in_ll */
     unsigned out_uses, out_call;
-    const void* in_ll;
+    const void* in_ll;           /* word image of A (NULL: A is an ordinary local tensor) */
     int in_ll_stride;
     unsigned in_uses, in_call;
-    int signal_counter;          /* 0: every reader of D is a qgemm_tp call using in_ll: skip the arrival counters AND the
-                                  * plain [M, n_total] image (only the word image is written) */
+    const unsigned* epoch;       /* device word holding the step number */
 } flute_b200_tp;
 
 FLUTE_B200_API int flute_b200_qgemm_tp(const void* A, const void* Q, const void* S, const void* table, const void* table2,
                         void* workspace, size_t workspace_bytes, int M, int N, int K, int num_bits, int group_size,
                         int tile_P, int dtype, int flags, int device, void* stream, const flute_b200_tp* tp);
-/* Arrivals ONE rank contributes to a gathered buffer per producing call: its output-tile count for N local columns. */
-FLUTE_B200_API int flute_b200_tp_tiles(int N, int num_bits);
 /* ++*epoch on `stream` (one tiny kernel): call once at the start of every step, before the step's first qgemm_tp. */
 FLUTE_B200_API int flute_b200_tp_advance(unsigned* epoch, int device, void* stream);
-/* Stream-ordered wait until `flag` has received (*epoch - 1) * per_step + offset arrivals: for consumers of a gathered
- * buffer that are not flute_b200_qgemm_tp calls (the copy of the step's result, another library's kernel). */
+/* After the producing call(s) on `stream`: system-scope fence, then +1 on flag_peers[r] for r < tp. */
+FLUTE_B200_API int flute_b200_tp_publish(unsigned* const* flag_peers, int tp, int device, void* stream);
+/* Stream-ordered wait until `flag` has received (*epoch - 1) * per_step + offset arrivals (one publish per rank and use:
+ * per_step = offset = tp for an output published once per step). */
 FLUTE_B200_API int flute_b200_tp_wait(const unsigned* flag, unsigned per_step, unsigned offset, const unsigned* epoch, int device,
                        void* stream);
 

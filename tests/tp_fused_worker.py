@@ -62,11 +62,10 @@ def main():
 
     shard = [{k: (*[t.to(dev) for t in parallel.shard_packed_linear(v[0], v[1], bits, rank, world, 32)], v[2] // world, v[3])
               for k, v in lin.items()} for lin in full]
-    # counters only where a non-qgemm consumer reads (the final `down`); every hand-over between qgemms rides on the
-    # {value, sequence} word image.  TP_TEST_COUNTERS=1: counters on every call as well (both protocols at once).
-    all_counters = os.environ.get("TP_TEST_COUNTERS", "0") == "1"
-    fg = parallel.FusedGather(dev, rank, world, [(name, M, N, layers, layers if all_counters else (1 if name == "down" else 0))
-                                                 for name, N, K in shapes], dtype)
+    # every hand-over between qgemms rides on the {value, sequence} word image; the plain image is kept only where a
+    # non-qgemm consumer reads (the final `down`), or everywhere with TP_TEST_COUNTERS=1
+    all_plain = os.environ.get("TP_TEST_COUNTERS", "0") == "1"
+    fg = parallel.FusedGather(dev, rank, world, [(name, M, N, layers) for name, N, K in shapes], dtype)
     flags = _lib.FLAG_PDL | _lib.FLAG_STATIC_WEIGHTS
 
     def tp_chain():
@@ -75,8 +74,8 @@ def main():
         for li, lin in enumerate(shard):
             for name, N, K in shapes:
                 Q, S, n_loc, _ = lin[name]
-                sig = True if all_counters else (name == "down" and li == layers - 1)
-                x = fg.qgemm(x, Q, S, table_d, table2_d, ws, name, n_loc, K, bits, group, flags, signal_counter=sig)
+                plain = True if all_plain else (name == "down" and li == layers - 1)
+                x = fg.qgemm(x, Q, S, table_d, table2_d, ws, name, n_loc, K, bits, group, flags, plain=plain)
         fg.end_step(shapes[-1][0])
         return x.clone()
 
