@@ -55,11 +55,17 @@ namespace dec {
 #define DPROF_T0(t) long long t = clock64()
 #define DPROF_ADD(acc, t) do { long long _n = clock64(); acc += _n - t; t = _n; } while (0)
 #define DPROF_OUT(slot, v) do { if (p.trace != nullptr) p.trace[blockIdx.x * 48 + (slot)] = (unsigned long long)(v); } while (0)
+#define DTRACE_ON(p) ((p).trace != nullptr)
+#define DABLATE(p, bit) (((p).ablate & (bit)) != 0)
 #else
 #define DPROF_DECL(...)
 #define DPROF_T0(t)
 #define DPROF_ADD(acc, t)
 #define DPROF_OUT(slot, v)
+// per-CTA time stamps and perf ablations are compiled out of the production kernel: code that never runs still costs (the
+// tensor-parallel paths, unused at tp = 1, cost every launch ~1 us until they moved into their own instantiation)
+#define DTRACE_ON(p) false
+#define DABLATE(p, bit) false
 #endif
 
 // NJ      pair fields per 32-bit word (accumulated output columns per packed row)
@@ -396,7 +402,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     const Range rg = cta_range(total, blockIdx.x, grid);
     const int spg_mask = (1 << p.gshift) - 1;
 
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 0] = globaltimer_ns();
+    if (DTRACE_ON(p) && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 0] = globaltimer_ns();
     if (!p.static_weights) pdl_wait_prior_grids();
     // Entry prefetch: the first TMA box cannot be requested before the barriers exist and the tensor map has been
     // fetched (~1 us after launch), and then pays a cold DRAM + page-walk latency on top.  The row addresses are plain
@@ -615,11 +621,11 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                             if (grp_first) wait(smem_u32(&ctl->p_empty[pslot]), (((uint32_t)f >> 1) & 1u) ^ 1u, p, DSITE_PEMPTY);
                             DPROF_ADD(mw_pempty, mt);
                             tc_fence_after();
-                            if (p.trace != nullptr && lane == 0 && mine == 0 && f == 0 && c == 0 && k == kb) p.trace[blockIdx.x * 48 + 3] = globaltimer_ns();
+                            if (DTRACE_ON(p) && lane == 0 && mine == 0 && f == 0 && c == 0 && k == kb) p.trace[blockIdx.x * 48 + 3] = globaltimer_ns();
                             if (elect_one()) {
                                 const uint32_t a_base = tmem + aslot * kACols;
                                 const uint32_t d_base = tmem + kPCol0 + pslot * kPCols;
-                                if (!(p.ablate & 1))
+                                if (!DABLATE(p, 1))
 #pragma unroll
                                 for (int j = 0; j < NJ; ++j) {
 #pragma unroll
@@ -683,7 +689,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             // the wait for the previous kernel.
             if (!kScaleWarpExists && p.static_weights) scale_step(tile, k, nb, last_blk);
             if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
-            if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
+            if (DTRACE_ON(p) && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
             if (TP && tp_in_ll() != nullptr) {
@@ -787,7 +793,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                     wait(smem_u32(&ctl->fix_full[n_fix]), 0u, p, DSITE_PFULL, 2);
                     ++n_fix;
                     if (!synced) { pdl_wait_prior_grids(); synced = true; }
-                    if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
+                    if (DTRACE_ON(p) && lane == 0) p.trace[blockIdx.x * 48 + 44] = globaltimer_ns();
                     const int tile_it0 = tile * p.k_iters;
                     const int first_cta = cta_of(total, tile_it0, grid);
                     const int contributors = cta_of(total, tile_it0 + p.k_iters - 1, grid) - first_cta + 1;
@@ -798,7 +804,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                         if (last) reinterpret_cast<int*>(p.workspace)[tile] = 0;   // self-resetting
                     }
                     last = __shfl_sync(0xffffffffu, last, 0);
-                    if (p.trace != nullptr && lane == 0) {
+                    if (DTRACE_ON(p) && lane == 0) {
                         p.trace[blockIdx.x * 48 + 45] = globaltimer_ns();
                         p.trace[blockIdx.x * 48 + 47] = (unsigned long long)((it - rg.it0) << 8 | last | (contributors << 20));
                     }
@@ -824,7 +830,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                                 }
                         }
                     }
-                    if (p.trace != nullptr && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
+                    if (DTRACE_ON(p) && lane == 0) p.trace[blockIdx.x * 48 + 46] = globaltimer_ns();
                 }
                 it += ke - kb;
             }
@@ -838,7 +844,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         int nloc[NFA];
 #pragma unroll
         for (int j = 0; j < NFA; ++j) nloc[j] = n_local<BITS, NJ>(L, fset * NFA + j, p.tile_p);
-        const bool do_apply = !(p.ablate & 4);
+        const bool do_apply = !DABLATE(p, 4);
         const uint32_t tmem = (rg.it1 > rg.it0) ? tmem_base_when_ready() : 0u;
         int pslot = 0;
         int stage = 0;                     // ring slot / phase of the stage the loop is at
@@ -923,7 +929,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             if (cur_blk >= 0) release_scales();
 
             // ------------------------------- epilogue ------------------------------------
-            if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 4] = globaltimer_ns();
+            if (DTRACE_ON(p) && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 4] = globaltimer_ns();
             if (!synced) { pdl_wait_prior_grids(); synced = true; }
             const bool full_k = (kb == 0) && (ke == p.k_iters);
             const int n_base = tile * TN;
@@ -952,11 +958,11 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->fix_full[n_fix]));
                 ++n_fix;
             }
-            if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 5] = globaltimer_ns();
+            if (DTRACE_ON(p) && warp == kApplyWarp0 && lane == 0 && it == rg.it0) p.trace[blockIdx.x * 48 + 5] = globaltimer_ns();
             DPROF_ADD(aw_epi, at);
             it += ke - kb;
         }
-        if (p.trace != nullptr && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 6] = globaltimer_ns();
+        if (DTRACE_ON(p) && warp == kApplyWarp0 && lane == 0) p.trace[blockIdx.x * 48 + 6] = globaltimer_ns();
         if (lane == 0 && warp == kApplyWarp0) { DPROF_OUT(40, aw_sc); DPROF_OUT(41, aw_pfull); DPROF_OUT(42, aw_work); DPROF_OUT(43, aw_epi); }
     } else {
         // ================================ dequantisers ==================================
@@ -978,13 +984,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
         }
-        if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 1] = globaltimer_ns();
+        if (DTRACE_ON(p) && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 1] = globaltimer_ns();
         const uint32_t tmem = (rg.it1 > rg.it0) ? tmem_base_when_ready() : 0u;
         const uint32_t lane4 = (uint32_t)lane * 4;
 
         const uint32_t wrow = (uint32_t)L * 128;
         const int xq = L & 7;
-        const bool do_dq = !(p.ablate & 2);
+        const bool do_dq = !DABLATE(p, 2);
         // DQG stage groups: with DQG == 2 the 16 warps split into two sets of 8 that convert alternate stages
         // (each warp: 4 quads = 16 k-pairs of its row).  During the conversion of a stage the shared-memory
         // crossbar is the limiter (16 B of packed words + 32 x 4 B of LUT reads per lane = 640 wavefronts per
@@ -1064,7 +1070,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     // ---- teardown ------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 7] = globaltimer_ns();
+    if (DTRACE_ON(p) && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 7] = globaltimer_ns();
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(*reinterpret_cast<volatile uint32_t*>(&ctl->tmem_base), F::TMEM_COLS);

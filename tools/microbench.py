@@ -77,7 +77,9 @@ def main():
             for i in range(ncopies):
                 launch(i)
             torch.cuda.synchronize()
-            if args.trace:
+            if args.trace and os.environ.get("FLUTE_B200_PROFILE") != "1":
+                print("   --trace needs the profiling build: FLUTE_B200_PROFILE=1 (python flute_b200/build.py --profile)")
+            elif args.trace:
                 # three PDL-chained launches, one trace buffer each: shows how far kernel i+1's CTAs get (start, set-up)
                 # while kernel i still runs, and the gap between kernel i's last exit and kernel i+1's first epilogue
                 import numpy as np

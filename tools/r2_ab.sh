@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-OUT=gpurun_out/r02ab3
+OUT=gpurun_out/r02ab4
 mkdir -p "$OUT"
 timeout 600 python -m pytest tests -m gpu -x -q -k "decode or pdl or golden or edge" > "$OUT/pytest.log" 2>&1; tail -3 "$OUT/pytest.log"
 for rep in 1 2; do
