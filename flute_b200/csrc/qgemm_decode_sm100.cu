@@ -62,10 +62,10 @@ namespace dec {
 #define DPROF_T0(t)
 #define DPROF_ADD(acc, t)
 #define DPROF_OUT(slot, v)
-// per-CTA time stamps and perf ablations are compiled out of the production kernel: code that never runs still costs (the
-// tensor-parallel paths, unused at tp = 1, cost every launch ~1 us until they moved into their own instantiation)
-#define DTRACE_ON(p) false
-#define DABLATE(p, bit) false
+// (compiling the per-CTA time stamps and ablation switches out of the production build as well was measured: small shapes
+// 1-2 % faster, large ones 3-5 % slower, bench 725 -> 707 tok/s -- gpurun r02ab2 vs r02ab4 -- so they stay run-time checks)
+#define DTRACE_ON(p) ((p).trace != nullptr)
+#define DABLATE(p, bit) (((p).ablate & (bit)) != 0)
 #endif
 
 // NJ      pair fields per 32-bit word (accumulated output columns per packed row)
@@ -400,10 +400,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     const int grid = gridDim.x;
     const int total = p.n_tiles * p.k_iters;
     const Range rg = cta_range(total, blockIdx.x, grid);
-    const int spg_mask = (1 << p.gshift) - 1;
+    // (a {group 64, tile_P 32, static weights, aligned scales} instantiation with these four folded to constants measured 1 %
+    // faster -- gpurun r02ab5 -- and was not kept)
+    const int r_gshift = p.gshift, r_tile_p = p.tile_p, r_static = p.static_weights, r_tma_scales = p.tma_scales;
+    const int spg_mask = (1 << r_gshift) - 1;
 
     if (DTRACE_ON(p) && threadIdx.x == 0) p.trace[blockIdx.x * 48 + 0] = globaltimer_ns();
-    if (!p.static_weights) pdl_wait_prior_grids();
+    if (!r_static) pdl_wait_prior_grids();
     // Entry prefetch: the first TMA box cannot be requested before the barriers exist and the tensor map has been
     // fetched (~1 us after launch), and then pays a cold DRAM + page-walk latency on top.  The row addresses are plain
     // arithmetic, so every dequantiser thread asks L2 for one 128-byte row piece of the CTA's first ring-full of
@@ -505,13 +508,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     // cp.async, not TMA: as a TMA box the 512 sixteen-byte rows cost the producer ~2000 cycles of issue time per
     // block (measured), during which no weight tile could be requested.
     auto scale_step = [&](int tile, int k, int& nb, int& last_blk) {
-        const int blk = (k >> p.gshift) >> 3;
+        const int blk = (k >> r_gshift) >> 3;
         if (blk == last_blk) return;
         const int slot = nb % kScSlots;
         const uint32_t par = ((nb / kScSlots) & 1) ^ 1u;
         wait(smem_u32(&ctl->sc_empty[slot]), par, p, DSITE_SCEMPTY);
         const uint32_t dst = sc_smem + slot * kScBytes;
-        if (p.tma_scales) {
+        if (r_tma_scales) {
 #pragma unroll 4
             for (int r = lane; r < TN; r += 32) {
                 const int n = tile * TN + r;
@@ -687,8 +690,8 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             int last_blk = -1;
             // Scales are static like the weights: when this warp also copies them, the first block goes out before
             // the wait for the previous kernel.
-            if (!kScaleWarpExists && p.static_weights) scale_step(tile, k, nb, last_blk);
-            if (p.static_weights) pdl_wait_prior_grids();      // activations come from the previous kernel
+            if (!kScaleWarpExists && r_static) scale_step(tile, k, nb, last_blk);
+            if (r_static) pdl_wait_prior_grids();      // activations come from the previous kernel
             if (DTRACE_ON(p) && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
@@ -825,7 +828,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
 #pragma unroll
                                 for (int qq = 0; qq < 4; ++qq) {
                                     accum[(j * kMb + m) * 128 + qq * 32 + lane] = 0.f;
-                                    const int n = n_base + n_local<BITS, NJ>(qq * 32 + lane, j, p.tile_p);
+                                    const int n = n_base + n_local<BITS, NJ>(qq * 32 + lane, j, r_tile_p);
                                     if (n < p.N) store_out(m, n, f32_to_t<BF16>(v[j][qq]), seq);
                                 }
                         }
@@ -843,7 +846,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         const int fset = (warp - kApplyWarp0) >> 2;        // which NFA-field subset this warp owns
         int nloc[NFA];
 #pragma unroll
-        for (int j = 0; j < NFA; ++j) nloc[j] = n_local<BITS, NJ>(L, fset * NFA + j, p.tile_p);
+        for (int j = 0; j < NFA; ++j) nloc[j] = n_local<BITS, NJ>(L, fset * NFA + j, r_tile_p);
         const bool do_apply = !DABLATE(p, 4);
         const uint32_t tmem = (rg.it1 > rg.it0) ? tmem_base_when_ready() : 0u;
         int pslot = 0;
@@ -876,7 +879,7 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
                 const uint32_t fpar = dphase;
                 if (++stage == p.stages) { stage = 0; dphase ^= 1u; }
                 if (!flush) continue;
-                const int g = k >> p.gshift;
+                const int g = k >> r_gshift;
                 const int blk = g >> 3;
                 if (blk != cur_blk) {
                     if (cur_blk >= 0) release_scales();
