@@ -67,7 +67,7 @@ constexpr int AS = 4;                // TMEM A slots (NF * 32 = 64 columns each)
 constexpr uint32_t kACols = NF * 32;
 constexpr uint32_t kDCol0 = AS * kACols;
 constexpr int DQG = 2;               // dequantiser sets: 8 warps each, alternate stages (one stage apart)
-constexpr size_t kPartBytes = (size_t)NF * kMb * 128 * 4;   // one partial tile: fp32 [16 warps][32 lanes][64]
+constexpr size_t kPartBytes = (size_t)NF * kMb * 128 * 4;   // one partial tile: fp32, float4 index = rows/4 * 512 + thread (16 warps x 32 lanes)
 
 struct Ctl {
     uint64_t full[kMaxStages];
@@ -559,16 +559,17 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty));
             } else {
                 // Partial K range.  This CTA's partial tile goes to one of its two scratch slots (slot 0: the
-                // segment starts at the CTA's first stage; slot 1: the CTA's last segment) as 64 consecutive floats
-                // per thread; the CTA that arrives last on the tile's counter sums every contributor's slot.
+                // segment starts at the CTA's first stage; slot 1: the CTA's last segment); the CTA that arrives last on
+                // the tile's counter sums every contributor's slot.  Slot layout: float4 number (c4 * 512 + thread) holds
+                // accumulator rows 4*c4 .. 4*c4+3 of that thread, so a warp's store or load is one 512-byte run.
                 const int tile_it0 = tile * p.k_iters;
                 const int first_cta = cta_of(p, tile_it0, grid);
                 const int last_cta = cta_of(p, tile_it0 + p.k_iters - 1, grid);
-                float* scratch = reinterpret_cast<float*>(p.workspace + p.scratch_offset);
-                const size_t part_floats = kPartBytes / 4;
-                const size_t my_off = (size_t)(warp * 32 + lane) * 64;
+                float4* scratch = reinterpret_cast<float4*>(p.workspace + p.scratch_offset);
+                const size_t part_f4 = kPartBytes / 16;
+                const int tid = warp * 32 + lane;
                 {
-                    float* dst = scratch + ((size_t)blockIdx.x * 2 + (it == rg.it0 ? 0 : 1)) * part_floats + my_off;
+                    float4* dst = scratch + ((size_t)blockIdx.x * 2 + (it == rg.it0 ? 0 : 1)) * part_f4 + tid;
 #pragma unroll 1
                     for (int mc = 0; mc < 64; mc += 16) {
                         uint32_t r[16];
@@ -576,7 +577,8 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                         tc_wait_ld();
 #pragma unroll
                         for (int x = 0; x < 16; x += 4)
-                            __stcg(reinterpret_cast<uint4*>(dst + mc + x), make_uint4(r[x], r[x + 1], r[x + 2], r[x + 3]));
+                            __stcg(reinterpret_cast<uint4*>(dst + (size_t)((mc + x) >> 2) * (kDqWarps * 32)),
+                                   make_uint4(r[x], r[x + 1], r[x + 2], r[x + 3]));
                     }
                 }
                 tc_fence_before();
@@ -593,18 +595,31 @@ qgemm_prefill_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 asm volatile("bar.sync 1, %0;" ::"n"(kDqWarps * 32) : "memory");
                 if (ctl->is_last) {
                     __threadfence();
+                    // contributor c's slot for this tile: 0 if its Stream-K share starts inside the tile, else 1
+                    auto slot_of = [&](int c) -> const float4* {
+                        const Range rc = cta_part(p, c, grid, 1);
+                        return scratch + ((size_t)c * 2 + (rc.it0 >= tile_it0 ? 0 : 1)) * part_f4 + tid;
+                    };
 #pragma unroll 1
                     for (int mc = 0; mc < rows_valid; mc += 16) {
                         float acc[16];
 #pragma unroll
                         for (int x = 0; x < 16; ++x) acc[x] = 0.f;
-                        for (int c = first_cta; c <= last_cta; ++c) {
-                            const Range rc = cta_part(p, c, grid, 1);
-                            const float* src = scratch + ((size_t)c * 2 + (rc.it0 >= tile_it0 ? 0 : 1)) * part_floats + my_off + mc;
+                        // two contributors' loads in flight at a time (a tile usually has two or three)
+#pragma unroll 1
+                        for (int c = first_cta; c <= last_cta; c += 2) {
+                            const float4* s0 = slot_of(c) + (size_t)(mc >> 2) * (kDqWarps * 32);
+                            const bool two = c + 1 <= last_cta;
+                            const float4* s1 = two ? slot_of(c + 1) + (size_t)(mc >> 2) * (kDqWarps * 32) : s0;
+                            float4 v0[4], v1[4];
 #pragma unroll
-                            for (int x = 0; x < 16; x += 4) {
-                                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + x));
-                                acc[x] += v.x; acc[x + 1] += v.y; acc[x + 2] += v.z; acc[x + 3] += v.w;
+                            for (int x = 0; x < 4; ++x) v0[x] = __ldcg(s0 + (size_t)x * (kDqWarps * 32));
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) v1[x] = two ? __ldcg(s1 + (size_t)x * (kDqWarps * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                acc[4 * x] += v0[x].x; acc[4 * x + 1] += v0[x].y; acc[4 * x + 2] += v0[x].z; acc[4 * x + 3] += v0[x].w;
+                                acc[4 * x] += v1[x].x; acc[4 * x + 1] += v1[x].y; acc[4 * x + 2] += v1[x].z; acc[4 * x + 3] += v1[x].w;
                             }
                         }
                         if (n < p.N) {

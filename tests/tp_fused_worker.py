@@ -1,7 +1,8 @@
 """Worker of tests/test_tp_fused_gpu.py -- launched by torchrun, one process per GPU (world_size 2..8).
 
 Column-shards a small chain of quantised linears, runs it with the exchange fused into the GEMM
-(flute_b200.parallel.FusedGather -> flute_b200_qgemm_tp: NVLink peer stores + arrival counters), eagerly and from a
+(flute_b200.parallel.FusedGather -> flute_b200_qgemm_tp: NVLink peer stores of {value, sequence} words; arrival
+counters only for the step's final plain image), eagerly and from a
 CUDA graph, and checks every rank's gathered result against the same chain computed on that GPU alone with the
 unsharded weights (flute_b200_qgemm), whose parity with the oracle the single-GPU tests establish.  Sharding is exact
 (tests/test_tp_gloo.py), whole-tile outputs are deterministic, so the two must agree to fp32-reduction-order noise."""
