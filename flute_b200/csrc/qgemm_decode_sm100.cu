@@ -785,6 +785,10 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
         // the CTA that arrives last reads the completed fp32 sums back, zeroes the scratch (workspace contract:
         // zero between launches) and writes the tile in T.  A contiguous Stream-K range has at most two partial
         // segments (its first and its last tile), one mbarrier each.
+        // (Measured alternative, gpurun r02h2 / r02h3: {sum, arrivals} pairs bumped by one returning packed atomic per
+        // contributor -- atom.add.v2.f32, no counter, no fix-up warp.  Correct (151 tests), but a returning atomic on an
+        // address 18 CTAs hit takes ~1.3 us, and the volume scales with M: M = 1 7.07 -> 6.88 us, M = 2 7.66 -> 12.3,
+        // M = 16 16.2 -> 40.2 on 4096x4096.  Fire-and-forget reductions + one counter per tile stay.)
         if (rg.it1 > rg.it0) {
             int n_fix = 0;
             bool synced = false;
@@ -1251,12 +1255,13 @@ int tp_wait_launch(const unsigned* flag, unsigned per_step, unsigned offset, con
 }
 
 bool qgemm_decode_supported(const QgemmArgs& a) {
-    // Dispatched automatically for M <= 4.  For 5 <= M <= 16 (4-bit) the 16-accumulator variant works (tests pin it
-    // with flute_b200_set_variant(2)) but measured slower than the general kernel on B200 (gate_up M=16: 48 vs 40 us,
-    // profiles/r01_microbench_final.log vs r01_general_kernel_microbench_before.log), so it is opt-in for now.
-    // 2-bit: eight accumulated fields per lane, so the register-resident accumulators stop at M = 4.
+    // 4-bit: M <= 16 (16 accumulators per field from M = 5 on).  In round 1 the 16-accumulator instantiation lost to the
+    // general kernel (gate_up M = 16: 48 vs 40 us); with this round's changes it wins at every M and shape measured
+    // (gpurun r02p2, us, general -> this kernel: qkv M = 5 15.9 -> 12.0, M = 16 20.4 -> 17.8; gate_up M = 16 40.2 -> 30.7;
+    // down M = 8 22.6 -> 18.3).  2-bit: eight accumulated fields per lane, so the register-resident accumulators stop at
+    // M = 4.
     if (a.M < 1) return false;
-    const int m_max = (a.num_bits == 4 && a.variant == 2) ? 16 : 4;
+    const int m_max = (a.num_bits == 4) ? 16 : 4;
     return (a.num_bits == 4 || a.num_bits == 2) && a.M <= m_max;
 }
 

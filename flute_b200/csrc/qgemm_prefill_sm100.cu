@@ -688,11 +688,16 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (total > 0x3fffffffLL || tiles >= (1 << 19)) return FB_ERR_SHAPE;
     int grid = a.num_sms;
     if (a.force_grid > 0) grid = a.force_grid;
-    // whole tiles per CTA unless that leaves more than ~10 % of the machine idle in the last wave
+    // Whole tiles per CTA, or Stream-K?  In stage units: whole tiles cost ceil(tiles / grid) * k_iters per CTA; Stream-K
+    // costs the even share plus the partial-tile hand-over (slot write, counter, the last arriver's reduction), which
+    // measured ~16 + k_iters / 8 stages (gpurun r02p2, M = 128 .. 4096 on the four Llama-3-8B shapes: e.g. 4096x4096
+    // M = 1024, 128 tiles: whole 38 us vs split 46; M = 512, 64 tiles: whole 38 us vs split 34).
     constexpr size_t kCounterBytes = 65536;
     {
         const long long waves = (tiles + grid - 1) / grid;
-        p.streamk = (tiles * 10 < waves * grid * 9) ? 1 : 0;
+        const long long whole_cost = waves * p.k_iters;
+        const long long split_cost = (total + grid - 1) / grid + 16 + p.k_iters / 8;
+        p.streamk = (split_cost < whole_cost) ? 1 : 0;
     }
     if (a.force_streamk >= 0) p.streamk = a.force_streamk;
     // Stream-K needs one arrival counter per tile in the 64 KB counter region; beyond that (very large M x N, where

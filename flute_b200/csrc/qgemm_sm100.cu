@@ -1104,6 +1104,7 @@ const char* qgemm_dispatch_name(int M, int num_bits, bool bf16) {
     QgemmArgs a{};
     a.M = M; a.num_bits = num_bits; a.bf16 = bf16; a.variant = -1;
     if (M >= 1 && qgemm_decode_supported(a)) {
+        if (num_bits == 4 && M > 4) return bf16 ? "fb::dec::qgemm_decode_kernel<4,bf16,MC=16>" : "fb::dec::qgemm_decode_kernel<4,f16,MC=16>";
         if (num_bits == 4) return M == 1 ? (bf16 ? "fb::dec::qgemm_decode_kernel<4,bf16,MC=1>" : "fb::dec::qgemm_decode_kernel<4,f16,MC=1>")
                                          : (bf16 ? "fb::dec::qgemm_decode_kernel<4,bf16,MC=4>" : "fb::dec::qgemm_decode_kernel<4,f16,MC=4>");
         return M == 1 ? (bf16 ? "fb::dec::qgemm_decode_kernel<2,bf16,MC=1>" : "fb::dec::qgemm_decode_kernel<2,f16,MC=1>")

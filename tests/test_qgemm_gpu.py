@@ -173,7 +173,7 @@ def test_decode_kernel_rows_and_groups(bits, M, group, dev, ws):
     """Every accumulator width (1 / 4 / 16 columns), every scale-group length, many CTAs per tile (Stream-K splits
     inside a scale group for group 128 / 256), scale rows both 16-byte aligned (cp.async) and not (K = 3584, g = 128)."""
     from flute_b200 import _lib
-    _lib.lib.flute_b200_set_variant(2)      # the decode kernel also for 5 <= M <= 16 (opt-in: see qgemm_decode_supported)
+    _lib.lib.flute_b200_set_variant(2)      # pin the decode kernel (also the automatic choice for these M)
     try:
         for (N, K, seed) in [(2048, 2048, 1), (1024, 3584, 2)]:
             if K % group:
@@ -251,6 +251,35 @@ def test_decode_kernel_schedules(pf, force, dev, ws):
         assert_close(run_cabi(c, dev, ws, force=force), oracle_qgemm(c), c["dtype"], f"decode W2 pf={pf} force={force}")
     finally:
         _lib.lib.flute_b200_set_variant(-1)
+
+
+@pytest.mark.parametrize("M", [1, 3, 9])
+def test_decode_split_k_hand_over_stress(M, dev):
+    """Split tiles are handed over through fire-and-forget fp32 reductions plus one arrival counter per tile; the last
+    arriver converts and re-zeroes the scratch (qgemm_decode_sm100.cu, fix-up warp).  A contribution lost or counted twice
+    would change a sum by ~1/contributors of its value: 300 back-to-back PDL launches with 18 (4096x4096) and ~19 (1024x8192
+    on 37 CTAs) contributors per tile must all agree with the oracle, agree with each other to fp32 summation-order noise,
+    and leave every counter and accumulator zero again."""
+    from flute_b200 import _lib, utils
+    ws = utils.make_workspace_streamk(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for (N, K, grid) in [(4096, 4096, 0), (1024, 8192, 37)]:
+        c = make_case(M, N, K, 4, 64, "bfloat16", seed=7 + M)
+        ref = oracle_qgemm(c)
+        A, Q, S, t2, tab = (c[k].to(dev) for k in ("A", "Q", "S", "table2", "table"))
+        outs = [torch.full((M, N), float("nan"), dtype=A.dtype, device=dev) for _ in range(300)]
+        for D in outs:
+            _lib.check(_lib.lib.flute_b200_qgemm_debug(A.data_ptr(), Q.data_ptr(), D.data_ptr(), S.data_ptr(), t2.data_ptr(),
+                                                       ws.data_ptr(), ws.numel(), M, N, K, 4, 64, 32, _lib.BF16, _lib.FLAG_PDL, 0, st,
+                                                       0, 0, grid, -1, None))
+        torch.cuda.synchronize()
+        _lib.check(_lib.lib.flute_b200_check(0))
+        assert_close(outs[0], ref, c["dtype"], f"hand-over M={M} {N}x{K}")
+        stack = torch.stack(outs).float()
+        assert not torch.isnan(stack).any()
+        spread = (stack - stack[0]).abs().max().item()
+        assert spread <= 2 ** -7 * stack[0].abs().max().item(), f"launches disagree by {spread}"     # one bf16 ulp of the largest value
+    assert int(ws.view(torch.int32)[: (64 << 20) // 4].abs().max().item()) == 0
 
 
 def test_decode_pdl_chain(dev, ws):
