@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--force-mb", type=int, default=0)
     ap.add_argument("--force-stages", type=int, default=0)
-    ap.add_argument("--force-grid", type=int, default=0)
+    ap.add_argument("--force-grid", default="0", help="CTAs per launch (0 = engine's choice); a comma list sweeps")
     ap.add_argument("--force-streamk", type=int, default=-1)
     ap.add_argument("--json", default=None)
     ap.add_argument("--variant", type=int, default=-1)
@@ -55,11 +55,14 @@ def main():
     table = torch.randn(2 ** bits, device=dev).to(dt)
     table2 = utils.make_qmap2_from_qmap(table)
     results = []
-    for (N, K) in SHAPE_SETS[args.shapes]:
+    shapes = SHAPE_SETS[args.shapes] if args.shapes in SHAPE_SETS else [tuple(int(v) for v in t.split("x")) for t in args.shapes.split(",")]
+    grids = [int(g) for g in str(args.force_grid).split(",")]
+    for (N, K) in shapes:
+      for force_grid in grids:
         for M in [int(m) for m in args.M.split(",")]:
             wbytes = N * K * bits // 8 + N * (K // group) * 2
             abytes = wbytes + M * K * 2 + M * N * 2 + (2 ** bits) * 2 + (4 ** bits) * 4
-            ncopies = max(2, min(64, (600 * 2 ** 20 + wbytes - 1) // wbytes))
+            ncopies = max(2, min(768, (600 * 2 ** 20 + wbytes - 1) // wbytes))
             Qs = [torch.randint(-32768, 32768, (N // 16 * bits, K), dtype=torch.int16, device=dev) for _ in range(ncopies)]
             Ss = [(torch.randn((N, K // group), device=dev) / K ** 0.5).to(dt) for _ in range(ncopies)]
             A = (torch.randn((M, K), device=dev)).to(dt)
@@ -70,7 +73,7 @@ def main():
                 rc = _lib.lib.flute_b200_qgemm_debug(
                     A.data_ptr(), Qs[i].data_ptr(), D.data_ptr(), Ss[i].data_ptr(), table2.data_ptr(), ws.data_ptr(),
                     ws.numel(), M, N, K, bits, group, 32, 1 if dt == torch.bfloat16 else 0, flags, 0,
-                    torch.cuda.current_stream().cuda_stream, args.force_mb, args.force_stages, args.force_grid,
+                    torch.cuda.current_stream().cuda_stream, args.force_mb, args.force_stages, force_grid,
                     args.force_streamk, None)
                 _lib.check(rc)
 
@@ -178,10 +181,10 @@ def main():
             tfl = 2.0 * M * N * K / us / 1e6
             _lib.check(_lib.lib.flute_b200_check(0))
             r = dict(N=N, K=K, M=M, bits=bits, us=us, gbs=gbs, hbm_frac=gbs / peaks["hbm_gbs"], tflops=tfl,
-                     tc_frac=tfl / peaks["bf16_tflops"], copies=ncopies)
+                     tc_frac=tfl / peaks["bf16_tflops"], copies=ncopies, grid=force_grid)
             results.append(r)
             print(f"N={N:6d} K={K:6d} M={M:5d} W{bits}: {us:9.2f} us  {gbs:8.1f} GB/s ({100 * r['hbm_frac']:5.1f}% HBM)  "
-                  f"{tfl:8.1f} TFLOP/s ({100 * r['tc_frac']:5.1f}% TC)  copies={ncopies}", flush=True)
+                  f"{tfl:8.1f} TFLOP/s ({100 * r['tc_frac']:5.1f}% TC)  copies={ncopies}" + (f"  grid={force_grid}" if force_grid else ""), flush=True)
             del Qs, Ss
             torch.cuda.empty_cache()
     if args.json:
