@@ -25,3 +25,6 @@ for l in open('gpurun_out/r02z/bench.json'):
         print(d.get('cpu_baseline'))
 PY
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > "$OUT/bench_reference.json" 2>> "$OUT/bench.err"; cat "$OUT/bench_reference.json" | cut -c1-400
+# 3-bit decode: per-shape time and role cycles of the general kernel (profiling build)
+FLUTE_B200_PROFILE=1 timeout 200 python tools/microbench.py --bits 3 --dtype fp16 --M 1 --shapes llama8b --trace 1 > "$OUT/w3_m1_profile.log" 2>&1
+cut -c1-150 "$OUT/w3_m1_profile.log" | head -120
