@@ -1084,28 +1084,6 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
     }
 }
 
-// CTAs per launch.  Default: every SM the launch may use, each with a contiguous share of the (tile, k) stages.  When
-// a CTA's share is only a few stages the launch is latency-bound, and shares that do not straddle tiles are worth a
-// few idle SMs: every CTA then has ONE partial segment (one hand-over) and a tile has exactly k_iters / share
-// contributors.  Swept per shape on B200 (gpurun r02g2, profiles/r02_experiments.md; us per launch, default -> aligned):
-// 4096x4096 7.05 -> 6.63 (128 CTAs x 4 stages), 3584x4096 7.16 -> 6.36 (112 x 4), 1024x4096 5.24 -> 4.86 (64 x 2);
-// large shapes lose (28672x4096 on 112 CTAs x 32 stages: 17.3 -> 19.5), hence the bounds on share and grid.
-static int pick_grid(long long total, int k_iters, int max_grid) {
-    if (total <= max_grid) {
-        // at most one stage per CTA: two per CTA halve the contributors per tile, as long as ~64 CTAs remain
-        if ((k_iters % 2) == 0 && total / 2 >= 64) return (int)(total / 2);
-        return (int)total;
-    }
-    for (int share = 2; share <= 8; ++share) {          // smallest share = largest grid first
-        if (k_iters % share != 0) continue;
-        const long long g = total / share;
-        if (g > max_grid) continue;
-        if (g * 4 >= (long long)max_grid * 3 || (share <= 4 && g * 5 >= (long long)max_grid * 3)) return (int)g;
-        break;                                          // larger shares only give smaller grids
-    }
-    return max_grid;
-}
-
 template <int BITS, bool BF16, int MC, bool TP>
 static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     using F = DCfg<BITS>;
@@ -1177,7 +1155,7 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
         grid = a.force_grid;
         if (grid > total) grid = (int)total;
     } else {
-        grid = pick_grid(total, p.k_iters, grid);
+        grid = decode_grid_for(total, p.k_iters, grid, true);
     }
 
     constexpr size_t kCounterBytes = 65536;

@@ -841,15 +841,19 @@ qgemm_sm100_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kDequantWarps * 32) : "memory");
                 if (ctl->is_last) {
+                    // one row at a time, every field of this warp in flight together (one L2 round trip per row, not
+                    // one per element: the decode shapes have a single row)
+                    for (int mi = 0; mi < rows_valid; ++mi) {
+                        float v[NJ];
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        if ((j % NG) != group) continue;
-                        const int n = n_base + nloc[j];
-                        for (int mi = 0; mi < rows_valid; ++mi) {
-                            float* src = accum + (j * p.mb + mi) * 128 + L;
-                            const float v = __ldcg(src);
-                            *src = 0.f;
-                            if (n < p.N) p.D[(size_t)(m_base + mi) * p.N + n] = f32_to_t<BF16>(v);
+                        for (int j = 0; j < NJ; ++j)
+                            if ((j % NG) == group) v[j] = __ldcg(accum + (j * p.mb + mi) * 128 + L);
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            if ((j % NG) != group) continue;
+                            accum[(j * p.mb + mi) * 128 + L] = 0.f;
+                            const int n = n_base + nloc[j];
+                            if (n < p.N) p.D[(size_t)(m_base + mi) * p.N + n] = f32_to_t<BF16>(v[j]);
                         }
                     }
                 }
@@ -1018,6 +1022,9 @@ static int launch_t(const QgemmArgs& a, cudaStream_t stream) {
     if (a.force_streamk >= 0) p.streamk = a.force_streamk;
     if (p.streamk) { if (grid > total) grid = (int)total; }
     else           { if (grid > tiles) grid = (int)tiles; }
+    // decode-shaped launches: a few SMs stay free for the next launch's late starters, shares aligned to tiles
+    if (!SMALL && p.streamk && a.force_grid <= 0 && a.M <= 16 && p.m_tiles == 1)
+        grid = decode_grid_for(total, p.k_iters, a.num_sms > 16 ? a.num_sms - 4 : a.num_sms, false);
 
     // workspace: [tile counters: fixed 64 KB][fp32 tile accumulators, one per output tile].  Both regions are
     // zero on entry (the caller zero-initialises the workspace once) and every kernel leaves what it touched

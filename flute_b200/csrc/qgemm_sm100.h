@@ -86,6 +86,31 @@ int qgemm_decode_launch(const QgemmArgs& a, cudaStream_t stream);
 inline size_t prefill_scratch_bytes(int num_sms) { return (size_t)num_sms * 2 * 131072 + 256; }
 bool qgemm_prefill_supported(const QgemmArgs& a);
 int qgemm_prefill_launch(const QgemmArgs& a, cudaStream_t stream);
+// CTAs per launch.  Default: every SM the launch may use, each with a contiguous share of the (tile, k) stages.  When
+// a CTA's share is only a few stages the launch is latency-bound, and shares that do not straddle tiles are worth a
+// few idle SMs: every CTA then has ONE partial segment (one hand-over) and a tile has exactly k_iters / share
+// contributors.  Swept per shape on B200 (gpurun r02g2, profiles/r02_experiments.md; us per launch, default -> aligned):
+// 4096x4096 7.05 -> 6.63 (128 CTAs x 4 stages), 3584x4096 7.16 -> 6.36 (112 x 4), 1024x4096 5.24 -> 4.86 (64 x 2);
+// large shapes lose (28672x4096 on 112 CTAs x 32 stages: 17.3 -> 19.5), hence the bounds on share and grid.  The general
+// kernel's decode-shaped launches (3-bit, M <= 16; gpurun r02g3) use the same rule: 28672x4096 W3 48.5 -> 41.0 (112 x 8),
+// 4096x14336 W3 35.8 -> 29.2 (112 x 4).
+inline int decode_grid_for(long long total, int k_iters, int max_grid, bool halve_single_stage_shares) {
+    if (total <= max_grid) {
+        if (!halve_single_stage_shares) return (int)total;
+        // at most one stage per CTA: two per CTA halve the contributors per tile, as long as ~64 CTAs remain
+        if ((k_iters % 2) == 0 && total / 2 >= 64) return (int)(total / 2);
+        return (int)total;
+    }
+    for (int share = 2; share <= 8; ++share) {          // smallest share = largest grid first
+        if (k_iters % share != 0) continue;
+        const long long g = total / share;
+        if (g > max_grid) continue;
+        if (g * 4 >= (long long)max_grid * 3 || (share <= 4 && g * 5 >= (long long)max_grid * 3)) return (int)g;
+        break;                                          // larger shares only give smaller grids
+    }
+    return max_grid;
+}
+
 int qgemm_max_mb(int bits);
 int tp_advance_launch(unsigned* epoch, cudaStream_t stream);
 int tp_publish_launch(unsigned* const* flags, int tp, cudaStream_t stream);
