@@ -691,7 +691,13 @@ qgemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const DecodePara
             // Scales are static like the weights: when this warp also copies them, the first block goes out before
             // the wait for the previous kernel.
             if (!kScaleWarpExists && r_static) scale_step(tile, k, nb, last_blk);
-            if (r_static) pdl_wait_prior_grids();      // activations come from the previous kernel
+            // Activations come from the previous kernel -- unless they are read from a {value, sequence} word image
+            // (tensor parallel): each word says by itself whether it is this hand-over's, so the launch does not wait for
+            // the producing grid to complete and flush (~1 us per launch), it consumes the words as they land.  Reuse of
+            // an image is safe without the wait: a launch can only write its output once it has ALL of its input, i.e.
+            // once every CTA of every rank's producing launch has finished reading that launch's own input.
+            const bool a_from_words = TP && tp_in_ll() != nullptr;
+            if (r_static && !a_from_words) pdl_wait_prior_grids();
             if (DTRACE_ON(p) && lane == 0) p.trace[blockIdx.x * 48 + 2] = globaltimer_ns();
             int stage = 0, astage = 0;
             uint32_t ephase = 1;
