@@ -33,6 +33,7 @@ EXPORTS = (
     "flute_b200_set_trace_buffer",
     "flute_b200_set_variant",
     "flute_b200_dispatch_name",
+    "flute_b200_decode_grid",
     "flute_b200_qgemm_tp",
     "flute_b200_tp_publish",
     "flute_b200_tp_advance",
@@ -102,6 +103,8 @@ def _load() -> ctypes.CDLL:
     lib.flute_b200_tp_wait.restype = _i
     lib.flute_b200_dispatch_name.argtypes = [_i, _i, _i]
     lib.flute_b200_dispatch_name.restype = ctypes.c_char_p
+    lib.flute_b200_decode_grid.argtypes = [ctypes.c_longlong, _i, _i, _i]
+    lib.flute_b200_decode_grid.restype = _i
     lib.flute_b200_check.argtypes = [_i]
     lib.flute_b200_check.restype = _i
     return lib

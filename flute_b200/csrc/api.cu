@@ -311,6 +311,13 @@ const char* flute_b200_dispatch_name(int M, int num_bits, int dtype) {
     return fb::qgemm_dispatch_name(M, num_bits, dtype == FLUTE_B200_BF16);
 }
 
+int flute_b200_decode_grid(long long total_stages, int k_iters, int num_sms, int num_bits) {
+    if (total_stages < 1 || k_iters < 1 || num_sms < 1) return 0;
+    const int max_grid = num_sms > 16 ? num_sms - 4 : num_sms;
+    // 2 / 4 bits: the decode kernel (may halve single-stage shares); 3 bits: the general kernel
+    return fb::decode_grid_for(total_stages, k_iters, max_grid, num_bits != 3);
+}
+
 const char* flute_b200_last_error(void) { return g_last_error; }
 
 const char* flute_b200_error_string(int code) {

@@ -175,6 +175,10 @@ FLUTE_B200_API int flute_b200_tp_wait(const unsigned* flag, unsigned per_step, u
 /* Name of the kernel the automatic dispatch of flute_b200_qgemm selects for (M, num_bits, dtype) -- reporting only
  * (bench.py's roofline.kernel); a static string. */
 FLUTE_B200_API const char* flute_b200_dispatch_name(int M, int num_bits, int dtype);
+/* CTAs a decode-shaped launch (M <= 16) uses for `total_stages` = column tiles x (K / 64) pipeline stages on a device with
+ * `num_sms` SMs -- reporting / test hook of the host-side schedule (csrc/qgemm_sm100.h decode_grid_for): all SMs but four,
+ * or fewer when a CTA's share of 2..8 stages can be aligned to tile boundaries.  No GPU needed. */
+FLUTE_B200_API int flute_b200_decode_grid(long long total_stages, int k_iters, int num_sms, int num_bits);
 
 FLUTE_B200_API const char* flute_b200_last_error(void);
 FLUTE_B200_API const char* flute_b200_error_string(int code);

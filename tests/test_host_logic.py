@@ -39,6 +39,54 @@ def test_version_and_workspace_formula():
     assert _lib.lib.flute_b200_max_batch_tile(4) == 64 and _lib.lib.flute_b200_max_batch_tile(5) < 0
 
 
+def test_dispatch_names():
+    """Which kernel the automatic dispatch picks (csrc/qgemm_sm100.cu qgemm_launch): the decode kernel for M <= 16 at 4 bits
+    and M <= 4 at 2 bits, the prefill kernel for 4-bit M > 16, the general kernel for the rest (all of 3-bit)."""
+    name = lambda M, bits, dt=_lib.BF16: _lib.lib.flute_b200_dispatch_name(M, bits, dt).decode()
+    assert name(1, 4) == "fb::dec::qgemm_decode_kernel<4,bf16,MC=1>"
+    assert name(4, 4, _lib.F16) == "fb::dec::qgemm_decode_kernel<4,f16,MC=4>"
+    assert name(5, 4) == name(16, 4) == "fb::dec::qgemm_decode_kernel<4,bf16,MC=16>"
+    assert name(17, 4) == name(4096, 4) == "fb::pre::qgemm_prefill_kernel<bf16>"
+    assert name(3, 2) == "fb::dec::qgemm_decode_kernel<2,bf16,MC=4>" and name(5, 2) == "fb::qgemm_sm100_kernel<2,bf16,LARGE>"
+    assert name(1, 3, _lib.F16) == name(64, 3, _lib.F16) == "fb::qgemm_sm100_kernel<3,f16,LARGE>"
+    assert name(1, 5) == "unsupported"
+
+
+def test_decode_grid_rule():
+    """CTAs per decode-shaped launch (csrc/qgemm_sm100.h decode_grid_for): the measured choices of
+    profiles/r02_decode_grid_sweep.log / r02_w3_grid_sweep.log, and the invariants of the rule."""
+    grid = _lib.lib.flute_b200_decode_grid
+    # (column tiles x k_iters, k_iters, SMs, bits) -> CTAs
+    table = [((8 * 64, 64, 148, 4), 128),      # 4096x4096: 4 stages per CTA, 16 contributors per tile
+             ((12 * 64, 64, 148, 4), 144),     # 6144x4096: no aligned share near the machine size
+             ((56 * 64, 64, 148, 4), 144),     # 28672x4096: bandwidth-bound, every SM but four
+             ((8 * 224, 224, 148, 4), 144),    # 4096x14336
+             ((6 * 64, 64, 148, 4), 96),       # 3072x4096 (tp 2)
+             ((7 * 64, 64, 148, 4), 112),      # 3584x4096 (tp 8)
+             ((4 * 224, 224, 148, 4), 128),    # 2048x14336 (tp 2): 7 stages per CTA
+             ((2 * 64, 64, 148, 4), 64),       # 1024x4096 (tp 4): two stages per CTA instead of one
+             ((1 * 64, 64, 148, 4), 64),       # 512x4096 (tp 8): one stage per CTA
+             ((2 * 64, 64, 148, 3), 128),      # 3-bit (2048-column tiles), 4096x4096: the general kernel keeps one stage per CTA
+             ((14 * 64, 64, 148, 3), 112),     # 3-bit 28672x4096
+             ((2 * 224, 224, 148, 3), 112),    # 3-bit 4096x14336
+             ((3 * 64, 64, 148, 3), 96)]       # 3-bit 6144x4096
+    for args, want in table:
+        assert grid(*args) == want, (args, grid(*args), want)
+    assert grid(0, 64, 148, 4) == 0 and grid(10, 0, 148, 4) == 0
+    for sms in (8, 16, 84, 132, 148):
+        max_grid = sms - 4 if sms > 16 else sms
+        for bits in (3, 4):
+            for k_iters in (1, 2, 7, 16, 56, 64, 112, 128, 224, 448):
+                for tiles in (1, 2, 3, 5, 8, 12, 20, 56, 112):
+                    total = tiles * k_iters
+                    g = grid(total, k_iters, sms, bits)
+                    assert 1 <= g <= min(total, max_grid)
+                    if g < min(total, max_grid):      # fewer CTAs than possible only for tile-aligned equal shares
+                        share = total // g
+                        assert total % g == 0 and k_iters % share == 0 and 2 <= share <= 8
+                        assert g * 5 >= min(total, max_grid) * 3 or (total <= max_grid and g >= 64)
+
+
 def _call_qgemm(M=1, N=512, K=256, bits=4, group=64, tile_p=32, dtype=0, ptr=0x1000):
     p = ctypes.c_void_p(ptr)
     return _lib.lib.flute_b200_qgemm(p, p, p, p, p, p, p, 1 << 20, M, N, K, bits, group, tile_p, dtype, 0, 0, None)
