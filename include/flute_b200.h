@@ -58,13 +58,14 @@ enum {
 /*
  * D[M,N] = A[M,K] . W_hat[K,N],  W_hat[k,n] = round_T(table2[code].{lo,hi} * S[n, k / group_size]).
  *
- * Numerics.  M >= 5 (general and prefill kernels): exactly the formula above, fp32 accumulation -- the reference's
- * arithmetic (packbits_utils.hpp:105,139).  M <= 4 at 2 / 4 bits (decode kernel): the group scale is applied to the fp32
- * partial sum of each group instead, D[m,n] = sum_g S[n,g] * (sum_{k in g} A[m,k] * table2[code(k,n)]), i.e. the product
- * table*S is NOT rounded to T first.  With a one-hot A this still yields round_T(table*S) exactly (bit-identical to
- * the reference's identity reconstruction; tested), for general A it differs from the M >= 5 result by rounding only
- * (bounded in tests/test_qgemm_gpu.py::test_decode_vs_prefill_numerics_bound: < 1.0e-3 fp16 / 5.5e-3 bf16 relative, inside
- * the reference's own 2.0e-3 / 1.1e-2 acceptance bound).  Consequence: results are not batch-invariant across M = 4 | 5.
+ * Numerics.  Prefill and general kernels (4-bit M > 16, 2-bit M > 4, all of 3-bit): exactly the formula above, fp32
+ * accumulation -- the reference's arithmetic (packbits_utils.hpp:105,139).  Decode kernel (4-bit M <= 16, 2-bit M <= 4): the
+ * group scale is applied to the fp32 partial sum of each group instead,
+ * D[m,n] = sum_g S[n,g] * (sum_{k in g} A[m,k] * table2[code(k,n)]), i.e. the product table*S is NOT rounded to T first.
+ * With a one-hot A this still yields round_T(table*S) exactly (bit-identical to the reference's identity reconstruction;
+ * tested), for general A it differs from the other kernels' result by rounding only (bounded in
+ * tests/test_qgemm_gpu.py::test_decode_vs_prefill_numerics_bound: < 1.0e-3 fp16 / 5.5e-3 bf16 relative, inside the
+ * reference's own 2.0e-3 / 1.1e-2 acceptance bound).  Consequence: 4-bit results are not batch-invariant across M = 16 | 17.
  * Split-K partial sums are added in fp32 in arrival order, so results are reproducible to fp32 reduction-order noise only
  * (as with the reference's Stream-K fix-up).
  *
@@ -139,7 +140,7 @@ FLUTE_B200_API int flute_b200_max_batch_tile(int num_bits);
  * sequence = (*epoch - 1) * uses + call + 1, with `uses` = producing calls per step of that buffer, `call` = index of the
  * producing call within the step (out_* for this call's output, in_* for A) and *epoch the step number (a device word,
  * >= 1, advanced once per step by flute_b200_tp_advance on the same stream).  CUDA-graph capturable; every rank issues
- * the same sequence of calls.  Decode shapes only (M <= 4 at 2 / 4 bits).  Every rank uses ONE layout: ll_peers[r] -
+ * the same sequence of calls.  M <= 4 only (2 / 4 bits).  Every rank uses ONE layout: ll_peers[r] -
  * out_peers[r] is the same for all r (one symmetric allocation per rank).
  *
  * Readers that are not qgemm_tp calls (the copy of the step's result, another library's kernel) take the plain image:
@@ -198,10 +199,11 @@ FLUTE_B200_API int flute_b200_check(int device);
  * complete, epilogue done, fix-up done, exit.  Pass NULL to switch tracing off. */
 FLUTE_B200_API void flute_b200_set_trace_buffer(void* device_ptr);
 
-/* Test hook: kernel selection for later qgemm launches: -1 automatic (default: decode kernel for M <= 4 at 2/4 bits,
- * prefill kernel for M > 16 at 4 bits, general kernel otherwise); 0 general kernel, LARGE footprint (1 CTA/SM);
- * 1 general kernel, SMALL footprint (2 CTAs/SM; M <= 16, 2/4 bits); 2 automatic, but the decode kernel also takes
- * 5 <= M <= 16 at 4 bits.  Bits 8..15: perf-ablation mask, bits 16..23: decode kernel's L2 prefetch distance + 1
+/* Test hook: kernel selection for later qgemm launches: -1 automatic (default: decode kernel for M <= 16 at 4 bits and
+ * M <= 4 at 2 bits, prefill kernel for M > 16 at 4 bits, general kernel otherwise); 0 general kernel, LARGE footprint
+ * (1 CTA/SM); 1 general kernel, SMALL footprint (2 CTAs/SM; M <= 16, 2/4 bits); 2 same as -1 (historical: the decode
+ * kernel's opt-in for 5 <= M <= 16).  Bits 8..15: perf-ablation mask, bits 16..23: decode kernel's L2 prefetch distance + 1,
+ * bits 24..30: SMs left idle per decode launch
  * (tools/microbench.py only). */
 FLUTE_B200_API void flute_b200_set_variant(int variant);
 

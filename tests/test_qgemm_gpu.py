@@ -219,6 +219,20 @@ def test_prefill_kernel_tails_and_schedules(M, force, dev, ws):
     assert_close(run_cabi(c, dev, ws, force=force), oracle_qgemm(c), c["dtype"], f"prefill M={M} force={force}")
 
 
+def test_prefill_more_tiles_than_counters(dev, ws):
+    """N = 57344 at M = 9600: 112 x 2 x 75 = 16800 output tiles, more than the 16384 arrival counters of the 64 KB counter
+    region.  The launcher must fall back to whole tiles per CTA (no counter is touched) instead of refusing the call -- the
+    reference accepts any M (round-1 advisory).  Checked on the first, a middle and the last activation rows."""
+    M, N, K = 9600, 57344, 512
+    c = make_case(M, N, K, 4, 64, "bfloat16", seed=31)
+    D = run_cabi(c, dev, ws)
+    assert not torch.isnan(D.float()).any()
+    for r0 in (0, 4736, M - 128):
+        sub = dict(c, A=c["A"][r0:r0 + 128].contiguous(), M=128)
+        assert_close(D[r0:r0 + 128].cpu(), oracle_qgemm(sub), c["dtype"], f"rows {r0}..{r0 + 128} of M={M} N={N}")
+    assert int(ws.view(torch.int32)[: (64 << 20) // 4].abs().max().item()) == 0
+
+
 def test_prefill_kernel_identity_bit_exact_fp16(dev, ws):
     K, N = 512, 1024
     c = make_case(K, N, K, 4, 64, "float16", seed=9, table="randn", identity=True)
@@ -422,23 +436,26 @@ def test_gpu_dequantiser_pinned_to_oracle_at_full_k(N, K, bits, dtype, dev):
 
 
 def test_decode_vs_prefill_numerics_bound(dev, ws, flute):
-    """M <= 4 (decode kernel) applies the group scale to the fp32 partial sum; M >= 5 rounds table*scale to T first, as
-    the reference does (packbits_utils.hpp:105,139; stated in include/flute_b200.h).  Same activation row, same
-    weights: the two results may differ by rounding only -- bounded here at half the reference's own tolerance so
-    that a later change cannot widen the gap unnoticed -- and each is within tolerance of the oracle."""
+    """The decode kernel (4-bit M <= 16) applies the group scale to the fp32 partial sum; the prefill kernel (M > 16) rounds
+    table*scale to T first, as the reference does (packbits_utils.hpp:105,139; stated in include/flute_b200.h).  Same
+    activation rows, same weights: the two results may differ by rounding only -- bounded here at half the reference's own
+    tolerance so that a later change cannot widen the gap unnoticed -- and each is within tolerance of the oracle."""
     from flute_b200.templates import default_template_id
     for dtype, bound in (("float16", 1.0e-3), ("bfloat16", 5.5e-3)):
-        c = make_case(5, 4096, 4096, 4, 64, dtype, seed=55, table="nf4")
+        c = make_case(17, 4096, 4096, 4, 64, dtype, seed=55, table="nf4")
         args = [c[k].to(dev) for k in ("Q", "S", "table", "table2")]
         A = c["A"].to(dev)
         tid = default_template_id(4)
-        D4 = flute.qgemm(A[:4].contiguous(), *args, ws, 4, 64, tid, 148)       # decode kernel
-        D5 = flute.qgemm(A, *args, ws, 4, 64, tid, 148)                        # general kernel (5 <= M <= 16)
+        D4 = flute.qgemm(A[:4].contiguous(), *args, ws, 4, 64, tid, 148)       # decode kernel, 4 accumulators per field
+        D16 = flute.qgemm(A[:16].contiguous(), *args, ws, 4, 64, tid, 148)     # decode kernel, 16 accumulators per field
+        D17 = flute.qgemm(A, *args, ws, 4, 64, tid, 148)                       # prefill kernel: the reference's rounding
         ref = oracle_qgemm(c)
         assert_close(D4, ref[:4], c["dtype"], f"M=4 {dtype}")
-        assert_close(D5, ref, c["dtype"], f"M=5 {dtype}")
-        e1, e2 = rel_errors(D4, D5[:4])
-        assert e1 < bound and e2 < bound, f"decode vs M=5 path on identical rows, {dtype}: {e1:.2e}"
+        assert_close(D16, ref[:16], c["dtype"], f"M=16 {dtype}")
+        assert_close(D17, ref, c["dtype"], f"M=17 {dtype}")
+        for D, rows in ((D4, 4), (D16, 16)):
+            e1, e2 = rel_errors(D, D17[:rows])
+            assert e1 < bound and e2 < bound, f"decode (M={rows}) vs prefill on identical rows, {dtype}: {e1:.2e}"
 
 
 @pytest.mark.parametrize("N,K", LLAMA3_8B[:4])
