@@ -67,7 +67,9 @@ class FusedGather:
         fg.begin_step();  y = fg.qgemm(x, Q_r, S_r, table, table2, ws, "qkv", n_loc, K, 4, 64, flags);  ...
         out = fg.qgemm(..., "down", ..., plain=True);  fg.end_step("down")           # `out` is data after end_step
 
-    Every rank must issue the same sequence of calls per step; each named buffer is written `uses` times per step.
+    Every rank must issue the same sequence of calls per step; each named buffer is written `uses` times per step, and no
+    call may read and write the same named buffer.  A call whose activations live in a gathered buffer does not wait for
+    the producing launch to finish: it consumes the words as they land.
     The tensor `qgemm` returns is a handle for the next `qgemm`; it holds current data only for calls made with
     `plain=True` and only after `end_step(name)` (publish + wait: the system-scope side of the exchange).
     """
@@ -136,6 +138,11 @@ class FusedGather:
         d.write_plain = 1 if plain else 0
         d.out_uses, d.out_call = o["uses"], o["calls"]
         src, elem_off = self._source_of(x)
+        if src is o:
+            # A launch that reads its activations from a word image does not wait for the producing grid (the words carry
+            # their own readiness); what keeps a later writer of an image behind its readers is that a launch needs ALL of
+            # its input before it can write anything -- which says nothing about a launch overwriting its own input.
+            raise ValueError(f"flute_b200: `{name}` cannot be both the activations and the output of one call")
         if src is None and not x.is_contiguous():
             raise ValueError("flute_b200: local activations must be contiguous")
         if src is not None:
