@@ -33,7 +33,7 @@
 // TMEM A slots before the activations exist, and the split-K fix-up runs in its own warp off the streaming path.
 //
 // Warp roles (persistent over a contiguous Stream-K range of (tile, k) stages).  DQ = dequantiser warps
-// (16); 832 threads for M <= 4, 928 for the opt-in 5 <= M <= 16 variant:
+// (16); 832 threads for M <= 4, 928 for the 16-accumulator 5 <= M <= 16 variant:
 //   warps 0..DQ-1    dequantisers: warp w owns TMEM lane quarter w%4 and a fixed set of 16-byte quads of its row
 //   warp DQ          TMA producer (packed weights, one 128-row x 64-k box per stage; optional L2 prefetch ahead)
 //   warps DQ+1,DQ+3  tcgen05.mma issuers (alternate scale groups; warp DQ+1 also allocates TMEM)
