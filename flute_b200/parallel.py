@@ -76,7 +76,6 @@ class FusedGather:
 
     def __init__(self, device: torch.device, rank: int, tp: int, outputs: Sequence[Tuple[str, int, int, int]],
                  dtype: torch.dtype, group: Optional[dist.ProcessGroup] = None) -> None:
-        import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
         self.device, self.rank, self.tp, self.dtype = device, rank, tp, dtype
@@ -87,12 +86,7 @@ class FusedGather:
             off += (M * n_total * 2 + 255) // 256 * 256
             ll_offs[name] = off
             off += (M * n_total * 8 + 255) // 256 * 256
-        self.buf = symm_mem.empty(off, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, group)
-        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        torch.cuda.synchronize(device)
-        dist.barrier(group)                      # every rank's images are zero before anyone's first store can land
+        self.buf, ptrs = self._allocate(off, group)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.out: Dict[str, dict] = {}
         for i, (name, M, n_total, uses) in enumerate(outputs):
@@ -103,11 +97,25 @@ class FusedGather:
                                   ll_peers=[p + ll_offs[name] for p in ptrs], flags=flags, my_flag=ptrs[rank] + 128 * i,
                                   calls=0, published=0)
 
+    def _allocate(self, nbytes: int, group) -> Tuple[torch.Tensor, list]:
+        """This rank's zeroed symmetric buffer and every rank's mapping of it (peer pointers, rank order)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        buf.zero_()
+        self.hdl = symm_mem.rendezvous(buf, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                      # every rank's images are zero before anyone's first store can land
+        return buf, ptrs
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
     def begin_step(self) -> None:
         for o in self.out.values():
             o["calls"] = 0
             o["published"] = 0
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        st = self._stream()
         self._lib.check(self._lib.lib.flute_b200_tp_advance(self.epoch.data_ptr(), self.device.index, st))
 
     def _source_of(self, x: torch.Tensor):
@@ -155,7 +163,7 @@ class FusedGather:
             d.in_uses, d.in_call = src["uses"], src["calls"] - 1
         d.epoch = self.epoch.data_ptr()
         code = _lib.BF16 if self.dtype == torch.bfloat16 else _lib.F16
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        st = self._stream()
         rc = _lib.lib.flute_b200_qgemm_tp(x.data_ptr(), Q.data_ptr(), S.data_ptr(), table.data_ptr(), table2.data_ptr(),
                                           workspace.data_ptr(), workspace.numel(), M, n_loc, K, num_bits, group_size, tile_P,
                                           code, flags, self.device.index, st, ctypes.byref(d))
@@ -169,7 +177,7 @@ class FusedGather:
         o = self.out[name]
         if o["published"]:
             raise ValueError(f"flute_b200: `{name}` already published in this step")
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        st = self._stream()
         lib = self._lib.lib
         self._lib.check(lib.flute_b200_tp_publish(o["flags"], self.tp, self.device.index, st))
         self._lib.check(lib.flute_b200_tp_wait(o["my_flag"], self.tp, self.tp, self.epoch.data_ptr(), self.device.index, st))
